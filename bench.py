@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- FRIEDA commit-path throughput on B200 (BASELINE.json metric: blobs committed/s and
+input GB/s vs the reference CPU path; % of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one pass of the hot path (pack -> circle-FFT LDE -> Merkle -> FRI layers with their
+commitments, i.e. FriProver::commit of src/proof.rs:38-57) over one batch of synthetic blobs:
+BASELINE config 3, `--blobs` independent 128 KiB blobs PER GPU (weak scaling, no collectives).
+
+  value : whole-job blobs/s with the inputs already resident in HBM (frieda_fri_commit_batch_device)
+  e2e   : same metric through the host-buffer C-ABI call (frieda_fri_commit_batch): pinned host
+          input -> H2D -> kernels -> D2H of the layer roots and last-layer polynomials, all timed
+  roofline     : the dominant kernel (Merkle bottom pass) against the measured HBM peak
+  passes       : the LDE and fold passes timed standalone against the HBM peak (BASELINE target)
+  cpu_baseline : the CPU oracle (a port of the reference's CpuBackend path) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOB_LEN = 131072                     # EIP-4844 blob size (BASELINE configs 2-4)
+CFG = (4, 0, 20, 20)                  # benches/proof.rs:5-12: blowup 2^4, log_last 0, 20 queries, pow 20
+SPLITMIX0 = 0x4652494544410000
+METRIC = "blobs_committed_per_s"
+UNIT = "blobs/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = samples in the upper half of the observed power range
+        thr = (min(power) + max(power)) / 2 if power else 0
+        loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def synth_blobs(n, rank_offset=0):
+    """n blobs of SplitMix64 bytes, blob b seeded with SPLITMIX0 + b -> (n, BLOB_LEN) uint8."""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    words = BLOB_LEN // 8
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, words + 1, dtype=np.uint64)[None, :]
+        s0 = (np.uint64(SPLITMIX0) + np.arange(rank_offset, rank_offset + n, dtype=np.uint64))[:, None]
+        z = (s0 + idx * np.uint64(0x9E3779B97F4A7C15)) & M
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.astype("<u8").view(np.uint8).reshape(n, BLOB_LEN)
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_sample(n_threads: int, blobs_per_thread: int):
+    """Times the CPU oracle (FRI commit phase per blob) on n_threads host threads."""
+    import numpy as np
+    from oracle import oracle as O
+    O.lib()
+    cfg = O.make_config(*CFG)
+    data = [synth_blobs(1, i)[0].tobytes() for i in range(n_threads)]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(blobs_per_thread):
+                O.fri_commit(data[i], None, cfg)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    if errs:
+        raise errs[0]
+    return n_threads * blobs_per_thread / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The Rust
+    crate cannot be built here (no cargo, stwo un-vendored), so this is the oracle port, which
+    mirrors stwo's CpuBackend structure (oracle/frieda_oracle.c header)."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_threads = max(1, min(cores, 64))
+    for _ in range(args.warmup):
+        cpu_sample(n_threads, 1)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt = cpu_sample(n_threads, 1)
+        t_total += dt
+        n_total += n_threads
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (M31) / u32 (BLAKE2s)",
+        "data": "synthetic", "input_gb_per_s": value * BLOB_LEN / 1e9,
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port",
+                         "sample": f"{n_threads} blobs per step (one per thread), {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, blobs_per_step=None):
+    return {
+        "workload": "C3: batch of independent 128 KiB blobs, commit + FRI layers "
+                    "(FriProver::commit: LDE, Merkle, 13 inner layers, last-layer poly)",
+        "blob_bytes": BLOB_LEN, "blobs_per_gpu_per_step": blobs_per_step if blobs_per_step else args.blobs,
+        "log_blowup": CFG[0], "log_last_layer_degree_bound": CFG[1], "parallelism": f"blob-sharded x{args.gpus}, no collectives",
+        "l2": "per-step input (512 MiB at 4096 blobs) and working set exceed the 126 MB L2",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="frieda_b200", choices=["frieda_b200", "reference"])
+    ap.add_argument("--blobs", type=int, default=4096, help="blobs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-passes", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import frieda_b200 as F
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: frieda_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = measured_peaks()
+
+    ctx = F.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
+    cfg = F.PcsConfig(*CFG)
+    n = args.blobs
+    L = 1 + ctx.n_inner_layers(BLOB_LEN, cfg)
+    host_np = synth_blobs(n, rank * n)
+    h_in = torch.from_numpy(host_np).pin_memory()
+    d_in = h_in.cuda(non_blocking=False)
+    d_roots = torch.zeros((n, L, 32), dtype=torch.uint8, device="cuda")
+    d_last = torch.zeros((n, 1, 4), dtype=torch.int32, device="cuda")
+    h_roots = torch.zeros((n, L, 32), dtype=torch.uint8).pin_memory()
+    h_last = torch.zeros((n, 1, 4), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.fri_commit_batch_ptr(d_in.data_ptr(), BLOB_LEN, BLOB_LEN, n, None, cfg, d_roots.data_ptr(),
+                                 d_last.data_ptr(), device=True)
+
+    def step_host():
+        ctx.fri_commit_batch_ptr(h_in.data_ptr(), BLOB_LEN, BLOB_LEN, n, None, cfg, h_roots.data_ptr(),
+                                 h_last.data_ptr(), device=False)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if profile:
+            ctx.profile_read(reset=True)
+            ctx.set_profiling(True)
+        launches0 = ctx.launch_count
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        prof = None
+        if profile:
+            ctx.set_profiling(False)
+            prof = ctx.profile_read(reset=True)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launch_count - launches0, prof
+
+    # parity spot check before timing: blob 0 of this rank against the golden/oracle-free invariant
+    # (first-layer root == commit root through the other entry point)
+    step_device()
+    stream.synchronize()
+    root0 = bytes(d_roots[0, 0].cpu().numpy())
+    assert root0 == ctx.commit(host_np[0], CFG[0]), "fri_commit layer-0 root != commit root"
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, prof = timed(step_device, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    ms_e2e, _, _ = timed(step_host, args.steps)
+    assert bytes(h_roots[0, 0].numpy()) == root0, "host-path root differs from device-path root"
+
+    total_blobs = n * world * args.steps
+    value = total_blobs / (ms_dev / 1e3)
+    e2e_value = total_blobs / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel, from the event-timed launches of the timed region
+    N = 1 << 18
+    dominant = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
+    dom_name, (dom_launches, dom_ms) = dominant
+    # algorithmic bytes per launch: bottom pass over layer 0 reads the 4 evaluation
+    # columns (16 B/leaf) and writes one 32-B subtree root per 1024 leaves, per blob
+    alg_bytes = {"merkle_bottom_cols": n * (16 * N + 32 * (N >> 10)),
+                 "fold_circle+merkle_bottom": n * (16 * N + 8 * N + 32 * (N >> 11)),
+                 }.get(dom_name)
+    roofline = None
+    if dom_name and dom_launches and alg_bytes:
+        per_launch_s = dom_ms / 1e3 / dom_launches
+        achieved = alg_bytes / per_launch_s / 1e9
+        roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": dom_ms / dom_launches, "share_of_step": dom_ms / ms_dev,
+                    "note": "INT32-issue bound (BLAKE2s), not HBM bound: see int_roofline and DESIGN.md"}
+    kernels = {k: {"launches": v[0], "total_ms": round(v[1], 3), "share": round(v[1] / ms_dev, 4)}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])} if prof else {}
+    # integer roofline: compressions per blob (SURVEY 8d, C2 commit+FRI = 1,048,498) x 976 SASS-level
+    # integer instructions, against 148 SMs x 4 SMSPs x 32 lanes x clock issue slots
+    compress_per_blob = 1048498
+    hashes_per_s = value / world * compress_per_blob
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6
+    int_roofline = {"hashes_per_s_per_gpu": hashes_per_s, "instr_per_hash": 976,
+                    "issue_slot_frac": hashes_per_s * 976 / issue_peak, "sm_mhz_used": sm_mhz}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (M31 field) / u32 (BLAKE2s)", "data": "synthetic",
+        "input_gb_per_s": value * BLOB_LEN / 1e9,
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * BLOB_LEN,
+                "d2h_bytes_per_step": n * (L * 32 + 16), "ms_per_step": ms_e2e / args.steps,
+                "input_gb_per_s": e2e_value * BLOB_LEN / 1e9},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "int_roofline": int_roofline,
+        "kernels": kernels,
+    }
+
+    if rank == 0 and not args.no_passes:
+        line["passes"] = standalone_passes(ctx, stream, torch, np, hbm_peak, peak_src)
+        line["single_blob_latency_ms"] = single_blob_latency(ctx, host_np, cfg)
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_threads = max(1, min(cores, 64))
+        v1, t1 = cpu_sample(1, 1)
+        per_thread = max(1, min(8, int(round(12.0 / max(t1, 1e-3)))))
+        v, dt = cpu_sample(n_threads, per_thread)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": n_threads, "kind": "port",
+                                "sample": f"{n_threads * per_thread} blobs ({per_thread} per thread) in {dt:.1f} s; "
+                                          f"1 thread: {v1:.3f} blobs/s",
+                                "single_thread_value": v1}
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+def standalone_passes(ctx, stream, torch, np, hbm_peak, peak_src):
+    """LDE and fold passes timed alone (BASELINE target: >= 60% of the HBM roofline).  Working sets
+    (>= 1 GiB) exceed L2, so no flush is needed between iterations."""
+    out = {}
+    nb, p, beta = 256, 14, 4
+    n_felts = 34953
+    D = p + beta
+    rng = np.random.default_rng(0)
+    coef = np.zeros((nb, 4 << p), dtype=np.uint32)
+    coef[:, :n_felts] = rng.integers(0, (1 << 31) - 1, (nb, n_felts), dtype=np.uint32)
+    d_coef = torch.from_numpy(coef.view(np.int32)).cuda()
+    d_eval = torch.empty((nb, 4 << D), dtype=torch.int32, device="cuda")
+    d_line = torch.empty((nb, 4 << (D - 1)), dtype=torch.int32, device="cuda")
+    d_line2 = torch.empty((nb, 4 << (D - 2)), dtype=torch.int32, device="cuda")
+    d_alpha = torch.from_numpy(rng.integers(0, (1 << 31) - 1, (nb, 4), dtype=np.uint32).view(np.int32)).cuda()
+    torch.cuda.synchronize()
+
+    def time_it(fn, iters=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    N = 1 << D
+    ms = time_it(lambda: ctx.pass_lde(d_coef.data_ptr(), p, beta, nb, n_felts, d_eval.data_ptr()))
+    b = nb * (16 * (1 << p) + 16 * N)
+    out["lde"] = {"algorithmic_bytes": b, "ms": ms, "achieved_gbs": b / ms / 1e6, "frac": b / ms / 1e6 / hbm_peak}
+    ms = time_it(lambda: ctx.pass_fold(d_eval.data_ptr(), D, True, nb, d_alpha.data_ptr(), d_line.data_ptr()))
+    b = nb * (16 * N + 8 * N)
+    out["fold_circle"] = {"algorithmic_bytes": b, "ms": ms, "achieved_gbs": b / ms / 1e6,
+                          "frac": b / ms / 1e6 / hbm_peak}
+    ms = time_it(lambda: ctx.pass_fold(d_line.data_ptr(), D - 1, False, nb, d_alpha.data_ptr(), d_line2.data_ptr()))
+    b = nb * (8 * N + 4 * N)
+    out["fold_line"] = {"algorithmic_bytes": b, "ms": ms, "achieved_gbs": b / ms / 1e6,
+                        "frac": b / ms / 1e6 / hbm_peak}
+    out["peak_gbs"] = hbm_peak
+    out["peak_source"] = peak_src
+    out["shape"] = f"{nb} blobs x 4 columns, poly_log {p}, blowup 2^{beta} (C2 shape)"
+    return out
+
+
+def single_blob_latency(ctx, host_np, cfg):
+    one = host_np[:1]
+    for _ in range(3):
+        ctx.fri_commit_batch(one, None, cfg)
+    t0 = time.perf_counter()
+    iters = 20
+    for _ in range(iters):
+        ctx.fri_commit_batch(one, None, cfg)
+    return (time.perf_counter() - t0) / iters * 1e3
+
+
+if __name__ == "__main__":
+    sys.exit(main())

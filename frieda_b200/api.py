@@ -1,0 +1,465 @@
+"""Host-side mirror of the reference crate's API over libfrieda_b200.so (ctypes).
+
+Same names and argument meaning as the reference (no Rust toolchain exists in this image, so
+the Rust shim of INTEGRATION.md cannot be compiled here; this module is the tested host side):
+
+    frieda::api::commit(data, log_blowup_factor) -> Commitment            src/lib.rs:31
+    frieda::api::generate_proof(data, seed, pcs_config) -> Proof          src/lib.rs:36
+    frieda::api::verify(proof, seed) -> bool                              src/lib.rs:41
+    frieda::proof::commit_and_generate_proof(...) -> (Commitment, Proof)  src/proof.rs:32
+
+There is no CPU fallback: every compute call needs the CUDA library and a CUDA device and raises
+FriedaError otherwise.  `verify` is host-only by design.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+ERR_PANIC, ERR_ALLOC, ERR_CUDA, ERR_ARG = -1, -2, -3, -4
+
+
+class FriedaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"frieda_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ReferencePanic(FriedaError):
+    """The reference implementation panics on this input (assert / unwrap)."""
+
+
+class QM31(C.Structure):
+    _fields_ = [("v", C.c_uint32 * 4)]
+
+    def tuple(self):
+        return tuple(int(x) for x in self.v)
+
+
+class PcsConfig(C.Structure):
+    """stwo PcsConfig { pow_bits, fri_config { log_blowup_factor, log_last_layer_degree_bound, n_queries } }."""
+    _fields_ = [
+        ("log_blowup_factor", C.c_uint32),
+        ("log_last_layer_degree_bound", C.c_uint32),
+        ("n_queries", C.c_uint64),
+        ("pow_bits", C.c_uint32),
+    ]
+
+    def __init__(self, log_blowup_factor=4, log_last_layer_degree_bound=0, n_queries=20, pow_bits=20):
+        super().__init__(log_blowup_factor, log_last_layer_degree_bound, n_queries, pow_bits)
+
+
+class LayerProof(C.Structure):
+    _fields_ = [
+        ("commitment", C.c_uint8 * 32),
+        ("n_fri_witness", C.c_uint32),
+        ("fri_witness", C.POINTER(QM31)),
+        ("n_hash_witness", C.c_uint32),
+        ("hash_witness", C.POINTER(C.c_uint8)),
+        ("n_column_witness", C.c_uint32),
+        ("column_witness", C.POINTER(C.c_uint32)),
+    ]
+
+
+class ProofStruct(C.Structure):
+    _fields_ = [
+        ("first_layer", LayerProof),
+        ("n_inner_layers", C.c_uint32),
+        ("inner_layers", C.POINTER(LayerProof)),
+        ("n_last_layer_poly", C.c_uint32),
+        ("last_layer_poly", C.POINTER(QM31)),
+        ("proof_of_work", C.c_uint64),
+        ("pcs_config", PcsConfig),
+        ("log_size_bound", C.c_uint32),
+        ("n_evaluations", C.c_uint32),
+        ("evaluations", C.POINTER(QM31)),
+    ]
+
+
+# every symbol include/frieda_b200.h declares
+EXPORTS = [
+    "frieda_ctx_create", "frieda_ctx_destroy", "frieda_last_error", "frieda_ctx_set_workspace_limit",
+    "frieda_ctx_launch_count", "frieda_ctx_stream", "frieda_ctx_set_profiling", "frieda_ctx_profile_read", "frieda_commit", "frieda_commit_batch",
+    "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
+    "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_proof_free",
+    "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_commit_split_local",
+    "frieda_merkle_combine", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
+    "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
+]
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    """Loads libfrieda_b200.so (building it with nvcc when stale).  Fails loudly if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.is_stale():
+        _build.build()
+    if not os.path.exists(path):
+        raise FriedaError(ERR_CUDA, f"{path} is missing: build it with `python -m frieda_b200.build` "
+                                    "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    vp, sz = C.c_void_p, C.c_size_t
+    cfgp, qp = C.POINTER(PcsConfig), C.POINTER(QM31)
+    pp = C.POINTER(ProofStruct)
+    sig = {
+        "frieda_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "frieda_ctx_destroy": (None, [vp]),
+        "frieda_last_error": (C.c_char_p, [vp]),
+        "frieda_ctx_set_workspace_limit": (C.c_int, [vp, sz]),
+        "frieda_ctx_launch_count": (C.c_uint64, [vp]),
+        "frieda_ctx_stream": (vp, [vp]),
+        "frieda_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
+        "frieda_ctx_profile_read": (C.c_long, [vp, C.c_char_p, sz, C.c_int]),
+        "frieda_commit": (C.c_int, [vp, vp, sz, C.c_uint32, u8p]),
+        "frieda_commit_batch": (C.c_int, [vp, vp, sz, sz, sz, C.c_uint32, vp]),
+        "frieda_commit_batch_device": (C.c_int, [vp, vp, sz, sz, sz, C.c_uint32, vp]),
+        "frieda_fri_n_inner_layers": (C.c_int, [sz, cfgp]),
+        "frieda_fri_commit_batch": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, vp]),
+        "frieda_fri_commit_batch_device": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, vp]),
+        "frieda_prove": (C.c_int, [vp, vp, sz, u64p, cfgp, u8p, C.POINTER(pp)]),
+        "frieda_prove_batch": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, C.POINTER(pp)]),
+        "frieda_verify": (C.c_int, [pp, u64p]),
+        "frieda_proof_free": (None, [pp]),
+        "frieda_proof_clone": (pp, [pp]),
+        "frieda_proof_serialize": (sz, [pp, vp, sz]),
+        "frieda_proof_deserialize": (C.c_int, [C.c_char_p, sz, C.POINTER(pp)]),
+        "frieda_commit_split_local": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+        "frieda_merkle_combine": (C.c_int, [vp, vp, C.c_uint32, u8p]),
+        "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
+        "frieda_pass_lde": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp]),
+        "frieda_pass_merkle": (C.c_int, [vp, vp, C.c_uint32, sz, vp, vp]),
+        "frieda_pass_fold": (C.c_int, [vp, vp, C.c_uint32, C.c_int, sz, vp, vp]),
+        "frieda_twiddles": (C.c_int, [vp, C.c_uint32, vp, vp]),
+        "frieda_debug_fetch": (C.c_long, [vp, C.c_int, sz, C.c_uint32, C.c_uint32, vp, sz]),
+        "frieda_ctx_set_debug_keep": (C.c_int, [vp, C.c_int]),
+    }
+    for name in EXPORTS:
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = sig[name]
+    _lib = L
+    return L
+
+
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        a = data
+        if a.dtype != np.uint8:
+            a = a.view(np.uint8)
+        return np.ascontiguousarray(a).reshape(-1)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+class Proof:
+    """Owns a frieda_proof*: fields mirror frieda::proof::Proof (src/proof.rs:19-26)."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+
+    def __del__(self):
+        ptr = getattr(self, "_ptr", None)
+        if ptr and _lib is not None:
+            _lib.frieda_proof_free(ptr)
+            self._ptr = None
+
+    @property
+    def c(self) -> ProofStruct:
+        return self._ptr.contents
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    def clone(self) -> "Proof":
+        p = load_library().frieda_proof_clone(self._ptr)
+        if not p:
+            raise FriedaError(ERR_ALLOC, "clone failed")
+        return Proof(p)
+
+    def serialize(self) -> bytes:
+        L = load_library()
+        n = L.frieda_proof_serialize(self._ptr, None, 0)
+        buf = (C.c_uint8 * n)()
+        L.frieda_proof_serialize(self._ptr, buf, n)
+        return bytes(buf)
+
+    @staticmethod
+    def deserialize(data: bytes) -> "Proof":
+        L = load_library()
+        p = C.POINTER(ProofStruct)()
+        rc = L.frieda_proof_deserialize(data, len(data), C.byref(p))
+        if rc:
+            raise FriedaError(rc, "malformed proof bytes")
+        return Proof(p)
+
+    # -- field views ---------------------------------------------------------------
+    @property
+    def proof_of_work(self) -> int:
+        return int(self.c.proof_of_work)
+
+    @proof_of_work.setter
+    def proof_of_work(self, v: int):
+        self.c.proof_of_work = v
+
+    @property
+    def log_size_bound(self) -> int:
+        return int(self.c.log_size_bound)
+
+    @property
+    def pcs_config(self) -> PcsConfig:
+        return self.c.pcs_config
+
+    @property
+    def evaluations(self) -> List[tuple]:
+        return [self.c.evaluations[i].tuple() for i in range(self.c.n_evaluations)]
+
+    def set_evaluation(self, i: int, value: Sequence[int]):
+        for j in range(4):
+            self.c.evaluations[i].v[j] = int(value[j])
+
+    def pop_evaluation(self):
+        self.c.n_evaluations -= 1
+
+    @property
+    def last_layer_poly(self) -> List[tuple]:
+        return [self.c.last_layer_poly[i].tuple() for i in range(self.c.n_last_layer_poly)]
+
+    @property
+    def first_layer_commitment(self) -> bytes:
+        return bytes(self.c.first_layer.commitment)
+
+    @property
+    def inner_layer_commitments(self) -> List[bytes]:
+        return [bytes(self.c.inner_layers[i].commitment) for i in range(self.c.n_inner_layers)]
+
+    @property
+    def n_inner_layers(self) -> int:
+        return int(self.c.n_inner_layers)
+
+
+class Context:
+    """One CUDA device + stream + twiddle cache + workspace (frieda_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.frieda_ctx_create(device, C.byref(h))
+        if rc:
+            msg = self._L.frieda_last_error(None)
+            raise FriedaError(rc, (msg or b"").decode() or "context creation failed (no CPU fallback exists)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.frieda_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc == 0:
+            return
+        msg = (self._L.frieda_last_error(self._h) or b"").decode()
+        if rc == ERR_PANIC:
+            raise ReferencePanic(rc, msg)
+        raise FriedaError(rc, msg)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.frieda_ctx_launch_count(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._L.frieda_ctx_stream(self._h) or 0)
+
+    def set_workspace_limit(self, nbytes: int):
+        self._check(self._L.frieda_ctx_set_workspace_limit(self._h, nbytes))
+
+    def set_profiling(self, on: bool):
+        self._check(self._L.frieda_ctx_set_profiling(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel name: (launches, total_ms)} measured with CUDA events on the context's stream."""
+        buf = C.create_string_buffer(1 << 16)
+        rc = self._L.frieda_ctx_profile_read(self._h, buf, len(buf), int(reset))
+        if rc < 0:
+            self._check(int(rc))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
+    def set_debug_keep(self, on: bool):
+        self._check(self._L.frieda_ctx_set_debug_keep(self._h, int(on)))
+
+    # -- commit --------------------------------------------------------------------
+    def commit(self, data, log_blowup_factor: int) -> bytes:
+        a = _as_u8(data)
+        out = (C.c_uint8 * 32)()
+        self._check(self._L.frieda_commit(self._h, a.ctypes.data, a.size, log_blowup_factor, out))
+        return bytes(out)
+
+    def commit_batch(self, blobs: np.ndarray, log_blowup_factor: int) -> np.ndarray:
+        """blobs: (n, blob_len) uint8, row-contiguous.  Returns (n, 32) uint8 roots."""
+        assert blobs.ndim == 2 and blobs.dtype == np.uint8 and blobs.strides[1] == 1
+        n, blob_len = blobs.shape
+        roots = np.zeros((n, 32), dtype=np.uint8)
+        self._check(self._L.frieda_commit_batch(self._h, blobs.ctypes.data, blob_len, blobs.strides[0], n,
+                                                log_blowup_factor, roots.ctypes.data))
+        return roots
+
+    def commit_batch_ptr(self, blobs_ptr: int, blob_len: int, stride: int, n: int, log_blowup_factor: int,
+                         roots_ptr: int, device: bool):
+        fn = self._L.frieda_commit_batch_device if device else self._L.frieda_commit_batch
+        self._check(fn(self._h, blobs_ptr, blob_len, stride, n, log_blowup_factor, roots_ptr))
+
+    # -- FRI commit phase ----------------------------------------------------------
+    def n_inner_layers(self, blob_len: int, cfg: PcsConfig) -> int:
+        rc = self._L.frieda_fri_n_inner_layers(blob_len, C.byref(cfg))
+        if rc < 0:
+            raise (ReferencePanic if rc == ERR_PANIC else FriedaError)(rc, "invalid shape for this config")
+        return rc
+
+    def fri_commit_batch(self, blobs: np.ndarray, seeds: Optional[Sequence[int]], cfg: PcsConfig):
+        """Returns (layer_roots (n, 1 + n_inner, 32) uint8, last_layer_poly (n, 2^log_last, 4) uint32)."""
+        assert blobs.ndim == 2 and blobs.dtype == np.uint8 and blobs.strides[1] == 1
+        n, blob_len = blobs.shape
+        L = 1 + self.n_inner_layers(blob_len, cfg)
+        roots = np.zeros((n, L, 32), dtype=np.uint8)
+        last = np.zeros((n, 1 << cfg.log_last_layer_degree_bound, 4), dtype=np.uint32)
+        sd = None
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+            assert sd.shape == (n,)
+        self._check(self._L.frieda_fri_commit_batch(self._h, blobs.ctypes.data, blob_len, blobs.strides[0], n,
+                                                    sd.ctypes.data if sd is not None else None, C.byref(cfg),
+                                                    roots.ctypes.data, last.ctypes.data))
+        return roots, last
+
+    def fri_commit_batch_ptr(self, blobs_ptr: int, blob_len: int, stride: int, n: int, seeds_ptr: Optional[int],
+                             cfg: PcsConfig, roots_ptr: int, last_ptr: int, device: bool):
+        fn = self._L.frieda_fri_commit_batch_device if device else self._L.frieda_fri_commit_batch
+        self._check(fn(self._h, blobs_ptr, blob_len, stride, n, seeds_ptr, C.byref(cfg), roots_ptr, last_ptr))
+
+    # -- proofs --------------------------------------------------------------------
+    def commit_and_generate_proof(self, data, seed: Optional[int], cfg: PcsConfig) -> Tuple[bytes, Proof]:
+        a = _as_u8(data)
+        root = (C.c_uint8 * 32)()
+        p = C.POINTER(ProofStruct)()
+        sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+        self._check(self._L.frieda_prove(self._h, a.ctypes.data, a.size, sp, C.byref(cfg), root, C.byref(p)))
+        return bytes(root), Proof(p)
+
+    def generate_proof(self, data, seed: Optional[int], cfg: PcsConfig) -> Proof:
+        return self.commit_and_generate_proof(data, seed, cfg)[1]
+
+    def prove_batch(self, blobs: np.ndarray, seeds: Optional[Sequence[int]], cfg: PcsConfig):
+        assert blobs.ndim == 2 and blobs.dtype == np.uint8 and blobs.strides[1] == 1
+        n, blob_len = blobs.shape
+        roots = np.zeros((n, 32), dtype=np.uint8)
+        arr = (C.POINTER(ProofStruct) * n)()
+        sd = None
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        self._check(self._L.frieda_prove_batch(self._h, blobs.ctypes.data, blob_len, blobs.strides[0], n,
+                                               sd.ctypes.data if sd is not None else None, C.byref(cfg),
+                                               roots.ctypes.data, arr))
+        return roots, [Proof(arr[i]) for i in range(n)]
+
+    # -- split blob ----------------------------------------------------------------
+    def commit_split_local(self, data, log_blowup_factor: int, rank: int, world: int, subroot_dev_ptr: int):
+        a = _as_u8(data)
+        self._check(self._L.frieda_commit_split_local(self._h, a.ctypes.data, a.size, log_blowup_factor, rank, world,
+                                                      subroot_dev_ptr))
+
+    def merkle_combine(self, subroots_dev_ptr: int, world: int) -> bytes:
+        out = (C.c_uint8 * 32)()
+        self._check(self._L.frieda_merkle_combine(self._h, subroots_dev_ptr, world, out))
+        return bytes(out)
+
+    # -- standalone passes / introspection ------------------------------------------
+    def twiddles(self, k: int):
+        tw = np.zeros(1 << k, dtype=np.uint32)
+        itw = np.zeros(1 << k, dtype=np.uint32)
+        self._check(self._L.frieda_twiddles(self._h, k, tw.ctypes.data, itw.ctypes.data))
+        return tw, itw
+
+    def pass_pack(self, d_blobs: int, blob_len: int, stride: int, n: int, d_coeffs: int):
+        self._check(self._L.frieda_pass_pack(self._h, d_blobs, blob_len, stride, n, d_coeffs))
+
+    def pass_lde(self, d_coeffs: int, poly_log: int, log_blowup: int, n: int, n_felts: int, d_evals: int):
+        self._check(self._L.frieda_pass_lde(self._h, d_coeffs, poly_log, log_blowup, n, n_felts, d_evals))
+
+    def pass_merkle(self, d_cols: int, log: int, n: int, d_tree: Optional[int], d_roots: int):
+        self._check(self._L.frieda_pass_merkle(self._h, d_cols, log, n, d_tree, d_roots))
+
+    def pass_fold(self, d_src: int, log: int, is_circle: bool, n: int, d_alpha: int, d_dst: int):
+        self._check(self._L.frieda_pass_fold(self._h, d_src, log, int(is_circle), n, d_alpha, d_dst))
+
+    def debug_fetch(self, what: int, blob: int, layer: int, level: int, nbytes: int) -> np.ndarray:
+        out = np.zeros(nbytes, dtype=np.uint8)
+        rc = self._L.frieda_debug_fetch(self._h, what, blob, layer, level, out.ctypes.data, nbytes)
+        if rc < 0:
+            self._check(int(rc))
+        return out[:rc]
+
+
+def verify_proof(proof: Proof, seed: Optional[int]) -> bool:
+    """frieda::proof::verify_proof (src/proof.rs:79-101).  Raises ReferencePanic where the reference
+    panics (too few evaluations, src/proof.rs:166-173)."""
+    L = load_library()
+    sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+    rc = L.frieda_verify(proof.ptr, sp)
+    if rc == ERR_PANIC:
+        raise ReferencePanic(rc, "reference panics on this proof")
+    if rc < 0:
+        raise FriedaError(rc, "verify failed")
+    return bool(rc)
+
+
+# ---- module-level functions with the reference's names (default context on device 0) ----------
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def commit(data, log_blowup_factor: int) -> bytes:
+    return default_context().commit(data, log_blowup_factor)
+
+
+def generate_proof(data, seed: Optional[int], pcs_config: PcsConfig) -> Proof:
+    return default_context().generate_proof(data, seed, pcs_config)
+
+
+def commit_and_generate_proof(data, seed: Optional[int], pcs_config: PcsConfig) -> Tuple[bytes, Proof]:
+    return default_context().commit_and_generate_proof(data, seed, pcs_config)
+
+
+def verify(proof: Proof, seed: Optional[int]) -> bool:
+    return verify_proof(proof, seed)

@@ -1,0 +1,222 @@
+// blake2s.cuh -- BLAKE2s compression held in registers, and the Fiat-Shamir channel.
+//
+// Merkle hashing (stwo vcs::blake2_merkle::Blake2sMerkleHasher::hash_node, called from
+// src/commit.rs:17-22 and inside FriProver via src/proof.rs:52) is the bare compression
+// function with an all-zero initial state and t = f = 0 (SURVEY finding 3).
+// The channel (stwo channel::Blake2sChannel; src/proof.rs:39-42,52,58-60,80-96) uses real
+// BLAKE2s-256 for mix_root / mix_felts / draw_random_bytes and the raw compression for mix_u64.
+// "parity unpinned": the channel byte layouts are restated from stwo's published algorithm
+// (SURVEY A.9); they live only in this header so they can be switched in one place.
+#pragma once
+#include <cstdint>
+
+#include "m31.cuh"
+
+namespace frieda {
+
+#if defined(__CUDA_ARCH__)
+FR_D uint32_t rotr16(uint32_t x) { return __byte_perm(x, 0, 0x1032); }
+FR_D uint32_t rotr8(uint32_t x) { return __byte_perm(x, 0, 0x0321); }
+FR_D uint32_t rotr12(uint32_t x) { return __funnelshift_r(x, x, 12); }
+FR_D uint32_t rotr7(uint32_t x) { return __funnelshift_r(x, x, 7); }
+#else
+inline uint32_t rotr_(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+inline uint32_t rotr16(uint32_t x) { return rotr_(x, 16); }
+inline uint32_t rotr8(uint32_t x) { return rotr_(x, 8); }
+inline uint32_t rotr12(uint32_t x) { return rotr_(x, 12); }
+inline uint32_t rotr7(uint32_t x) { return rotr_(x, 7); }
+#endif
+
+#define FR_B2S_IV0 0x6A09E667u
+#define FR_B2S_IV1 0xBB67AE85u
+#define FR_B2S_IV2 0x3C6EF372u
+#define FR_B2S_IV3 0xA54FF53Au
+#define FR_B2S_IV4 0x510E527Fu
+#define FR_B2S_IV5 0x9B05688Cu
+#define FR_B2S_IV6 0x1F83D9ABu
+#define FR_B2S_IV7 0x5BE0CD19u
+
+#define FR_G(a, b, c, d, x, y) \
+  do {                         \
+    a = a + b + (x);           \
+    d = rotr16(d ^ a);         \
+    c = c + d;                 \
+    b = rotr12(b ^ c);         \
+    a = a + b + (y);           \
+    d = rotr8(d ^ a);          \
+    c = c + d;                 \
+    b = rotr7(b ^ c);          \
+  } while (0)
+
+#define FR_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+  do {                                                                                  \
+    FR_G(v0, v4, v8, v12, m[s0], m[s1]);                                                \
+    FR_G(v1, v5, v9, v13, m[s2], m[s3]);                                                \
+    FR_G(v2, v6, v10, v14, m[s4], m[s5]);                                               \
+    FR_G(v3, v7, v11, v15, m[s6], m[s7]);                                               \
+    FR_G(v0, v5, v10, v15, m[s8], m[s9]);                                               \
+    FR_G(v1, v6, v11, v12, m[s10], m[s11]);                                             \
+    FR_G(v2, v7, v8, v13, m[s12], m[s13]);                                              \
+    FR_G(v3, v4, v9, v14, m[s14], m[s15]);                                              \
+  } while (0)
+
+// h <- compress(h, m, t0, t1, f0, f1).  Fully unrolled; with constant zeros in h / m the
+// compiler folds the corresponding adds away (leaf messages carry 4 words, grind messages 2).
+FR_HD void blake2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
+                            uint32_t f1) {
+  uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+  uint32_t v8 = FR_B2S_IV0, v9 = FR_B2S_IV1, v10 = FR_B2S_IV2, v11 = FR_B2S_IV3;
+  uint32_t v12 = FR_B2S_IV4 ^ t0, v13 = FR_B2S_IV5 ^ t1, v14 = FR_B2S_IV6 ^ f0, v15 = FR_B2S_IV7 ^ f1;
+  FR_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  FR_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+  FR_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
+  FR_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
+  FR_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
+  FR_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
+  FR_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
+  FR_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
+  FR_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
+  FR_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
+  h[0] ^= v0 ^ v8;
+  h[1] ^= v1 ^ v9;
+  h[2] ^= v2 ^ v10;
+  h[3] ^= v3 ^ v11;
+  h[4] ^= v4 ^ v12;
+  h[5] ^= v5 ^ v13;
+  h[6] ^= v6 ^ v14;
+  h[7] ^= v7 ^ v15;
+}
+
+// Merkle leaf over the 4 coordinate columns: hash_node(None, [c0, c1, c2, c3]).
+FR_HD void merkle_hash_leaf(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[8]) {
+  uint32_t m[16] = {c0, c1, c2, c3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  blake2s_compress(out, m, 0, 0, 0, 0);
+}
+// Merkle inner node: hash_node(Some((left, right)), []); m = left || right.
+FR_HD void merkle_hash_node(const uint32_t m[16], uint32_t out[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  blake2s_compress(out, m, 0, 0, 0, 0);
+}
+
+// ---- Blake2sChannel ------------------------------------------------------
+struct Channel {
+  uint32_t digest[8];  // 32 digest bytes as little-endian words
+  uint32_t n_sent;     // reset whenever the digest changes (u64 in stwo; < 2^32 here)
+};
+FR_HD void channel_init(Channel &c) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.digest[i] = 0;
+  c.n_sent = 0;
+}
+FR_HD void b2s256_init(uint32_t h[8]) {
+  h[0] = FR_B2S_IV0 ^ 0x01010020u;
+  h[1] = FR_B2S_IV1;
+  h[2] = FR_B2S_IV2;
+  h[3] = FR_B2S_IV3;
+  h[4] = FR_B2S_IV4;
+  h[5] = FR_B2S_IV5;
+  h[6] = FR_B2S_IV6;
+  h[7] = FR_B2S_IV7;
+}
+// BLAKE2s-256 of exactly one 64-byte block given as 16 LE words.
+FR_HD void b2s256_block64(const uint32_t m[16], uint32_t out[8]) {
+  b2s256_init(out);
+  blake2s_compress(out, m, 64, 0, 0xFFFFFFFFu, 0);
+}
+// mix_root: digest = H(digest || root)
+FR_HD void channel_mix_root(Channel &c, const uint32_t root[8]) {
+  uint32_t m[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    m[i] = c.digest[i];
+    m[8 + i] = root[i];
+  }
+  b2s256_block64(m, c.digest);
+  c.n_sent = 0;
+}
+// mix_u64: digest = compress(digest, [lo, hi, 0 x 14], 0, 0, 0, 0)   (raw compression)
+FR_HD void channel_mix_u64(Channel &c, uint64_t n) {
+  uint32_t m[16] = {(uint32_t)n, (uint32_t)(n >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  blake2s_compress(c.digest, m, 0, 0, 0, 0);
+  c.n_sent = 0;
+}
+// mix_felts: digest = H(digest || felts as 4 x u32 LE each); any length (multi-block).
+FR_HD void channel_mix_felts(Channel &c, const QM31 *felts, uint32_t n) {
+  uint32_t h[8];
+  b2s256_init(h);
+  uint32_t total_words = 8 + 4 * n;  // message length in words
+  uint32_t m[16];
+  uint32_t w = 0;  // words consumed
+  uint64_t t = 0;
+  for (;;) {
+    uint32_t take = total_words - w;
+    bool last = take <= 16;
+    if (!last) take = 16;
+    for (uint32_t i = 0; i < 16; i++) {
+      uint32_t idx = w + i;
+      uint32_t val = 0;
+      if (i < take) val = idx < 8 ? c.digest[idx] : felts[(idx - 8) >> 2].v[(idx - 8) & 3];
+      m[i] = val;
+    }
+    w += take;
+    t += 4ull * take;
+    blake2s_compress(h, m, (uint32_t)t, (uint32_t)(t >> 32), last ? 0xFFFFFFFFu : 0u, 0);
+    if (last) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.digest[i] = h[i];
+  c.n_sent = 0;
+}
+// draw_random_bytes: H(digest || n_sent as u64 LE || 24 zero bytes); n_sent += 1
+FR_HD void channel_draw_random_words(Channel &c, uint32_t out[8]) {
+  uint32_t m[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = c.digest[i];
+  m[8] = c.n_sent;
+#pragma unroll
+  for (int i = 9; i < 16; i++) m[i] = 0;
+  c.n_sent += 1;
+  b2s256_block64(m, out);
+}
+// draw_felt: first 4 of 8 base felts; retry until all 8 words < 2P (p ~ 2^-28 per draw).
+FR_HD QM31 channel_draw_felt(Channel &c) {
+  for (;;) {
+    uint32_t u[8];
+    channel_draw_random_words(c, u);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ok = ok && (u[i] < 2u * P31);
+    if (!ok) continue;
+    QM31 r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.v[i] = u[i] >= P31 ? u[i] - P31 : u[i];
+    return r;
+  }
+}
+// trailing zeros of the u128 built little-endian from digest bytes 0..16
+FR_HD uint32_t digest_trailing_zeros(const uint32_t d[8]) {
+  uint32_t tz = 0;
+  for (int i = 0; i < 4; i++) {
+    uint32_t w = d[i];
+    if (w == 0) {
+      tz += 32;
+      continue;
+    }
+#if defined(__CUDA_ARCH__)
+    return tz + (uint32_t)(__ffs((int)w) - 1);
+#else
+    uint32_t k = 0;
+    while (!(w & 1u)) {
+      w >>= 1;
+      k++;
+    }
+    return tz + k;
+#endif
+  }
+  return 128;
+}
+
+}  // namespace frieda

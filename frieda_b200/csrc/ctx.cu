@@ -1,0 +1,1020 @@
+// ctx.cu -- context, wave planning and the C ABI entry points of libfrieda_b200.so.
+//
+// Call sequences mirror the reference glue:
+//   frieda_commit*      : src/commit.rs:11-23   pack -> LDE -> Merkle root
+//   frieda_fri_commit*  : src/proof.rs:38-57    + channel, FriProver::commit
+//   frieda_prove*       : src/proof.rs:32-77    + grind, mix_u64, decommit, evaluations
+// A batched call is cut into waves that fit the device workspace; within a wave every kernel is
+// launched once over all blobs (grid.y / grid.z = blob).  There is no CPU fallback: all stages run
+// as CUDA kernels on the context's stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/frieda_b200.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace frieda;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Geom {
+  size_t len = 0;
+  uint32_t n_felts = 0, p = 0, beta = 0, D = 0;
+  // proof shape
+  uint32_t log_last = 0, last_log = 0, n_inner = 0, n_layers = 0;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+struct Plan {
+  Geom g;
+  size_t B = 0;
+  uint32_t nq = 0;  // n_queries (prove)
+  bool keep = false, prove = false, fri = false;
+  size_t in_stride = 0;  // bytes between staged blobs
+  size_t o_in = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
+  size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
+  size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
+  size_t o_best = 0, o_unsolved = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
+         o_evals = 0;
+  size_t total = 0;
+};
+
+uint32_t layer_log(const Geom &g, uint32_t layer) { return g.D - layer; }
+
+size_t tree_slots(uint32_t d, bool keep) {
+  // kept trees hold every level; truncated trees only the levels above the bottom pass
+  // (tail layers: just the root in slot 1)
+  if (keep) return (size_t)2 << d;
+  uint32_t chunk = d < 10 ? d : 10;
+  return (size_t)2 << (d - chunk);
+}
+
+}  // namespace
+
+struct frieda_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  size_t ws_limit = 0;
+  // twiddle cache
+  bool tw_valid = false;
+  uint32_t tw_K = 0;
+  uint32_t *d_tw = nullptr, *d_itw = nullptr;
+  GenPowers gp;
+  // workspace arena
+  uint8_t *arena = nullptr;
+  size_t arena_bytes = 0;
+  // small result staging
+  uint8_t *d_scratch = nullptr;  // 4 KiB
+  // per-kernel timing with CUDA events on the launching stream (bench.py's roofline)
+  bool profiling = false;
+  struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  void prof_begin(const char *name) {
+    if (!profiling) return;
+    ProfRec r{name, nullptr, nullptr};
+    for (cudaEvent_t *e : {&r.a, &r.b}) {
+      if (!prof_pool.empty()) {
+        *e = prof_pool.back();
+        prof_pool.pop_back();
+      } else {
+        cudaEventCreate(e);
+      }
+    }
+    cudaEventRecord(r.a, stream);
+    prof_recs.push_back(r);
+  }
+  void prof_end() {
+    if (!profiling || prof_recs.empty()) return;
+    cudaEventRecord(prof_recs.back().b, stream);
+  }
+  // introspection
+  bool debug_keep = false;
+  bool have_last = false;
+  Plan last;
+  std::vector<uint64_t> last_nonces;
+
+  int fail(cudaError_t e, const char *what, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s [ctx.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
+    err = buf;
+    cudaGetLastError();
+    return FRIEDA_ERR_CUDA;
+  }
+  int fail_arg(const char *msg, int code = FRIEDA_ERR_ARG) {
+    err = msg;
+    return code;
+  }
+};
+
+#define CU(call)                                                            \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) return ctx->fail(e_, #call, __LINE__);           \
+  } while (0)
+#define KL(name, call, n)                                                   \
+  do {                                                                      \
+    ctx->prof_begin(name);                                                  \
+    cudaError_t e_ = (call);                                                \
+    ctx->prof_end();                                                        \
+    if (e_ != cudaSuccess) return ctx->fail(e_, #call, __LINE__);           \
+    ctx->launches += (n);                                                   \
+  } while (0)
+
+namespace {
+
+int make_geom(frieda_ctx *ctx, size_t len, uint32_t log_blowup, Geom &g) {
+  if (len >= ((size_t)1 << 31)) return ctx->fail_arg("input longer than 2^31 bytes is not supported");
+  g.len = len;
+  g.n_felts = (uint32_t)((len * 8 + 29) / 30);
+  uint32_t lg = g.n_felts ? host::ceil_log2(g.n_felts) : 0;  // src/utils.rs:23 (f64 log2 of 0 casts to 0)
+  if (lg < 2) lg = 2;
+  g.p = lg - 2;
+  g.beta = log_blowup;
+  uint64_t D = (uint64_t)g.p + log_blowup;
+  if (D == 0) return ctx->fail_arg("reference panics: Coset::half_odds(poly_log + log_blowup - 1) underflows",
+                                   FRIEDA_ERR_PANIC);
+  if (D > 28) return ctx->fail_arg("domain larger than 2^28 is not supported");
+  g.D = (uint32_t)D;
+  return FRIEDA_OK;
+}
+
+int make_geom_fri(frieda_ctx *ctx, size_t len, const frieda_pcs_config *cfg, Geom &g) {
+  int rc = make_geom(ctx, len, cfg->log_blowup_factor, g);
+  if (rc) return rc;
+  g.log_last = cfg->log_last_layer_degree_bound;
+  // commit_last_layer: assert_eq!(evaluation.len(), config.last_layer_domain_size())
+  if ((uint64_t)g.p < 1 + (uint64_t)g.log_last)
+    return ctx->fail_arg("reference panics: polynomial too small for log_last_layer_degree_bound", FRIEDA_ERR_PANIC);
+  g.last_log = g.log_last + g.beta;
+  g.n_inner = g.p - 1 - g.log_last;
+  g.n_layers = g.n_inner + 1;
+  if (g.D < 3) return ctx->fail_arg("FRI over a domain smaller than 8 points is not supported");
+  if (g.last_log > TAIL_LAST_MAX)
+    return ctx->fail_arg("log_last_layer_degree_bound + log_blowup_factor > 9 is not supported");
+  if (g.n_layers > 30) return ctx->fail_arg("too many FRI layers");
+  return FRIEDA_OK;
+}
+
+int ensure_twiddles(frieda_ctx *ctx, uint32_t K) {
+  if (ctx->tw_valid && ctx->tw_K >= K) return FRIEDA_OK;
+  if (ctx->d_tw) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_tw);
+    cudaFree(ctx->d_itw);
+    ctx->d_tw = ctx->d_itw = nullptr;
+    ctx->tw_valid = false;
+  }
+  size_t bytes = sizeof(uint32_t) << K;
+  CU(cudaMalloc(&ctx->d_tw, bytes));
+  CU(cudaMalloc(&ctx->d_itw, bytes));
+  KL("twiddles", launch_twiddles(ctx->stream, ctx->gp, K, ctx->d_tw, ctx->d_itw), 1);
+  ctx->tw_K = K;
+  ctx->tw_valid = true;
+  return FRIEDA_OK;
+}
+
+TwiddleTable table(const frieda_ctx *ctx) { return TwiddleTable{ctx->d_tw, ctx->d_itw, ctx->tw_K}; }
+
+int ensure_arena(frieda_ctx *ctx, size_t bytes) {
+  if (ctx->arena_bytes >= bytes) return FRIEDA_OK;
+  if (ctx->arena) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    ctx->have_last = false;
+  }
+  cudaError_t e = cudaMalloc(&ctx->arena, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "device workspace allocation of %zu bytes failed", bytes);
+    ctx->err = buf;
+    return FRIEDA_ERR_ALLOC;
+  }
+  ctx->arena_bytes = bytes;
+  return FRIEDA_OK;
+}
+
+size_t workspace_budget(frieda_ctx *ctx) {
+  if (ctx->ws_limit) return ctx->ws_limit;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    return (size_t)8 << 30;
+  }
+  return (size_t)((double)(free_b + ctx->arena_bytes) * 0.8);
+}
+
+// Lays out one wave of B blobs.  stage_input: reserve a device copy of the input bytes.
+void layout(Plan &pl, size_t B, bool stage_input) {
+  const Geom &g = pl.g;
+  pl.B = B;
+  Bump bp;
+  pl.in_stride = align_up(g.len ? g.len : 1, 16);
+  if (stage_input) pl.o_in = bp.take(B * pl.in_stride);
+  pl.o_coef = bp.take(B * ((size_t)16 << g.p));
+  const uint32_t n_cols_layers = pl.fri ? g.n_layers + 1 : 1;
+  for (uint32_t l = 0; l < n_cols_layers; l++) {
+    uint32_t d = (!pl.fri || l < g.n_layers) ? layer_log(g, l) : g.last_log;
+    pl.cols_stride[l] = (size_t)4 << d;
+    pl.o_cols[l] = bp.take(B * pl.cols_stride[l] * 4);
+  }
+  const uint32_t n_trees = pl.fri ? g.n_layers : 1;
+  for (uint32_t l = 0; l < n_trees; l++) {
+    pl.tree_stride[l] = tree_slots(layer_log(g, l), pl.keep);
+    pl.o_tree[l] = bp.take(B * pl.tree_stride[l] * 32);
+  }
+  pl.o_roots = bp.take(B * (size_t)(pl.fri ? g.n_layers : 1) * 32);
+  if (pl.fri) {
+    pl.o_chan = bp.take(B * sizeof(Channel));
+    pl.o_alpha = bp.take(B * g.n_layers * sizeof(QM31));
+    pl.o_last = bp.take(B * (sizeof(QM31) << g.log_last));
+    pl.o_err = bp.take(256);
+    pl.o_seeds = bp.take(B * 8);
+  }
+  if (pl.prove) {
+    pl.o_best = bp.take(B * 8);
+    pl.o_unsolved = bp.take(256);
+    pl.o_totals = bp.take(256);
+  }
+  pl.total = bp.off;
+}
+
+// per-wave extras of the prove path that depend on n_queries
+void layout_prove_tail(Plan &pl, uint32_t n_queries) {
+  Bump bp;
+  bp.off = pl.total;
+  pl.nq = n_queries;
+  pl.o_queries = bp.take(pl.B * n_queries * 4);
+  pl.o_nuniq = bp.take(pl.B * 4);
+  pl.o_counts = bp.take(pl.B * pl.g.n_layers * 2 * 4);
+  pl.o_offsets = bp.take(pl.B * pl.g.n_layers * 2 * 8);
+  pl.o_evals = bp.take(pl.B * n_queries * sizeof(QM31));
+  pl.total = bp.off;
+}
+
+size_t pick_wave(frieda_ctx *ctx, Plan &pl, size_t n, bool stage_input, uint32_t n_queries) {
+  size_t budget = workspace_budget(ctx);
+  layout(pl, 1, stage_input);
+  if (pl.prove) layout_prove_tail(pl, n_queries);
+  size_t per_blob = pl.total + 4096;
+  size_t B = budget / per_blob;
+  if (B < 1) B = 1;
+  if (B > n) B = n;
+  if (B > 32768) B = 32768;
+  layout(pl, B, stage_input);
+  if (pl.prove) layout_prove_tail(pl, n_queries);
+  return B;
+}
+
+template <class T>
+T *at(frieda_ctx *ctx, size_t off) {
+  return reinterpret_cast<T *>(ctx->arena + off);
+}
+
+// Merkle tree over an existing or fused-folded layer: bottom chunks, middle passes, top.
+int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channel *chan, uint8_t *roots,
+                size_t roots_stride) {
+  const Geom &g = pl.g;
+  const uint32_t d = layer_log(g, layer);
+  MerkleBottomParams mp;
+  std::memset(&mp, 0, sizeof mp);
+  TwiddleTable tt = table(ctx);
+  if (src == SRC_COLS) {
+    mp.src_cols = at<uint32_t>(ctx, pl.o_cols[layer]);
+    mp.src_stride = pl.cols_stride[layer];
+  } else {
+    mp.src_cols = at<uint32_t>(ctx, pl.o_cols[layer - 1]);
+    mp.src_stride = pl.cols_stride[layer - 1];
+    mp.dst_cols = at<uint32_t>(ctx, pl.o_cols[layer]);
+    mp.dst_stride = pl.cols_stride[layer];
+    mp.alpha = at<QM31>(ctx, pl.o_alpha) + (layer - 1);
+    mp.alpha_stride = g.n_layers;
+    // circle fold of the log-D evaluation: pairs (x, y) of the block of length 2^(D-2);
+    // line fold of a log-(d+1) layer: block of length 2^d
+    mp.itw_blk = src == SRC_FOLD_CIRCLE ? tt.iblk(1u << (g.D - 2)) : tt.iblk(1u << d);
+  }
+  mp.tree = at<uint8_t>(ctx, pl.o_tree[layer]);
+  mp.tree_stride = pl.tree_stride[layer];
+  mp.log = d;
+  mp.chunk_log = d < 10 ? d : 10;
+  mp.levels = mp.chunk_log;
+  mp.src_level = d;
+  mp.write_all = pl.keep ? 1 : 0;
+  KL(src == SRC_COLS ? "merkle_bottom_cols" : src == SRC_FOLD_CIRCLE ? "fold_circle+merkle_bottom" : "fold_line+merkle_bottom",
+     launch_merkle_bottom(ctx->stream, src, mp, pl.B), 1);
+  uint32_t u = d - mp.chunk_log;
+  while (u > 10) {
+    MerkleBottomParams mm = mp;
+    mm.src_cols = nullptr;
+    mm.dst_cols = nullptr;
+    mm.alpha = nullptr;
+    mm.log = u;
+    mm.src_level = u;
+    mm.chunk_log = (u - 10) < 10 ? (u - 10 < 1 ? 1 : u - 10) : 10;
+    mm.levels = mm.chunk_log;
+    KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, pl.B), 1);
+    u -= mm.chunk_log;
+  }
+  QM31 *alpha = chan ? at<QM31>(ctx, pl.o_alpha) + layer : nullptr;
+  KL("merkle_top", launch_merkle_top(ctx->stream, mp.tree, mp.tree_stride, u, pl.keep ? 1 : 0, roots, roots_stride, chan, alpha,
+                       g.n_layers, pl.B),
+     1);
+  return FRIEDA_OK;
+}
+
+CPoint half_initial_point(const Geom &g) { return host::point_from_index(half_odds_index(g.D - 1, 0)); }
+
+// pack + LDE of the wave's blobs (device pointer d_in, stride bytes) into cols[0]
+int lde_wave(frieda_ctx *ctx, const Plan &pl, const uint8_t *d_in, size_t stride) {
+  const Geom &g = pl.g;
+  uint32_t *coef = at<uint32_t>(ctx, pl.o_coef);
+  KL("pack", launch_pack(ctx->stream, d_in, g.len, stride, pl.B, g.n_felts, g.p, coef), 1);
+  KL("lde", launch_lde(ctx->stream, coef, at<uint32_t>(ctx, pl.o_cols[0]), g.p, g.beta, pl.B, g.n_felts, table(ctx),
+                half_initial_point(g)),
+     (g.p > 15 ? 2 : 1));
+  return FRIEDA_OK;
+}
+
+int stage_in(frieda_ctx *ctx, const Plan &pl, const uint8_t *h_blobs, size_t stride, const uint8_t **d_in,
+             size_t *d_stride) {
+  uint8_t *dst = at<uint8_t>(ctx, pl.o_in);
+  const Geom &g = pl.g;
+  if (g.len) {
+    if (stride == g.len && pl.in_stride == g.len) {
+      CU(cudaMemcpyAsync(dst, h_blobs, pl.B * g.len, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      CU(cudaMemcpy2DAsync(dst, pl.in_stride, h_blobs, stride, g.len, pl.B, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  *d_in = dst;
+  *d_stride = pl.in_stride;
+  return FRIEDA_OK;
+}
+
+// ---- commit ----------------------------------------------------------------------------
+int commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride, size_t n, uint32_t log_blowup,
+                uint8_t *roots_out, bool device_io) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if ((!blobs && len) || !roots_out) return ctx->fail_arg("null pointer");
+  if (n == 0) return FRIEDA_OK;
+  if (n > 1 && stride < len) return ctx->fail_arg("blob_stride smaller than blob_len");
+  CU(cudaSetDevice(ctx->device));
+  Plan pl;
+  int rc = make_geom(ctx, len, log_blowup, pl.g);
+  if (rc) return rc;
+  pl.keep = false;
+  if (pl.g.D >= 3 && (rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
+  size_t B = pick_wave(ctx, pl, n, !device_io, 0);
+  if ((rc = ensure_arena(ctx, pl.total))) return rc;
+  ctx->have_last = false;
+  for (size_t b0 = 0; b0 < n; b0 += B) {
+    size_t nb = std::min(B, n - b0);
+    Plan w = pl;
+    w.B = nb;
+    const uint8_t *d_in = blobs + b0 * stride;
+    size_t d_stride = stride;
+    if (!device_io && (rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
+    if ((rc = lde_wave(ctx, w, d_in, d_stride))) return rc;
+    uint8_t *d_roots = at<uint8_t>(ctx, w.o_roots);
+    if ((rc = commit_tree(ctx, w, 0, SRC_COLS, nullptr, d_roots, 32))) return rc;
+    CU(cudaMemcpyAsync(roots_out + b0 * 32, d_roots, nb * 32, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    if (!device_io) CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return FRIEDA_OK;
+}
+
+// ---- FRI commit phase for one wave; leaves all state in the arena ------------------------
+int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_stride, const uint64_t *d_seeds) {
+  const Geom &g = w.g;
+  int rc;
+  if ((rc = lde_wave(ctx, w, d_in, d_stride))) return rc;
+  Channel *chan = at<Channel>(ctx, w.o_chan);
+  KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
+  CU(cudaMemsetAsync(at<int>(ctx, w.o_err), 0, sizeof(int), ctx->stream));
+  uint8_t *roots = at<uint8_t>(ctx, w.o_roots);
+  const size_t roots_stride = (size_t)g.n_layers * 32;
+  uint32_t layer = 0;
+  while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
+    int src = layer == 0 ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
+    if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
+    layer++;
+  }
+  const uint32_t s = layer;  // first layer handled by the tail (== n_layers: only the last evaluation)
+  const uint32_t s_log = s < g.n_layers ? layer_log(g, s) : g.last_log;
+  if (s >= 1) {
+    const uint32_t src_log = layer_log(g, s - 1);
+    KL("fold", launch_fold(ctx->stream, at<uint32_t>(ctx, w.o_cols[s - 1]), w.cols_stride[s - 1], src_log, s - 1 == 0,
+                   at<QM31>(ctx, w.o_alpha) + (s - 1), g.n_layers, table(ctx), at<uint32_t>(ctx, w.o_cols[s]),
+                   w.cols_stride[s], w.B),
+       1);
+  }
+  TailParams tp;
+  std::memset(&tp, 0, sizeof tp);
+  for (uint32_t l = 0; l <= g.n_layers; l++) {
+    tp.cols[l] = at<uint32_t>(ctx, w.o_cols[l]);
+    tp.cols_stride[l] = w.cols_stride[l];
+    if (l < g.n_layers) {
+      tp.tree[l] = at<uint8_t>(ctx, w.o_tree[l]);
+      tp.tree_stride[l] = w.tree_stride[l];
+    }
+  }
+  tp.write_all = w.keep ? 1 : 0;
+  tp.start_layer = s;
+  tp.start_log = s_log;
+  tp.last_log = g.last_log;
+  tp.log_last = g.log_last;
+  tp.inv_last_n = m31_inv(1u << g.last_log);
+  tp.roots = roots;
+  tp.roots_stride = roots_stride;
+  tp.chan = chan;
+  tp.alpha = at<QM31>(ctx, w.o_alpha);
+  tp.alpha_stride = g.n_layers;
+  tp.last_poly = at<QM31>(ctx, w.o_last);
+  tp.error_flag = at<int>(ctx, w.o_err);
+  tp.tt = table(ctx);
+  KL("fri_tail", launch_tail(ctx->stream, tp, w.B), 1);
+  return FRIEDA_OK;
+}
+
+int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride, size_t n,
+                    const uint64_t *seeds, const frieda_pcs_config *cfg, uint8_t *roots_out,
+                    frieda_qm31 *last_poly_out, bool device_io) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if ((!blobs && len) || !cfg || !roots_out || !last_poly_out) return ctx->fail_arg("null pointer");
+  if (n == 0) return FRIEDA_OK;
+  if (n > 1 && stride < len) return ctx->fail_arg("blob_stride smaller than blob_len");
+  CU(cudaSetDevice(ctx->device));
+  Plan pl;
+  int rc = make_geom_fri(ctx, len, cfg, pl.g);
+  if (rc) return rc;
+  pl.fri = true;
+  pl.keep = ctx->debug_keep;
+  if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
+  size_t B = pick_wave(ctx, pl, n, !device_io, 0);
+  if ((rc = ensure_arena(ctx, pl.total))) return rc;
+  const Geom &g = pl.g;
+  const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (size_t b0 = 0; b0 < n; b0 += B) {
+    size_t nb = std::min(B, n - b0);
+    Plan w = pl;
+    w.B = nb;
+    const uint8_t *d_in = blobs + b0 * stride;
+    size_t d_stride = stride;
+    const uint64_t *d_seeds = nullptr;
+    if (!device_io) {
+      if ((rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
+      if (seeds) {
+        CU(cudaMemcpyAsync(at<uint64_t>(ctx, w.o_seeds), seeds + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_seeds = at<uint64_t>(ctx, w.o_seeds);
+      }
+    } else if (seeds) {
+      d_seeds = seeds + b0;
+    }
+    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds))) return rc;
+    CU(cudaMemcpyAsync(roots_out + b0 * g.n_layers * 32, at<uint8_t>(ctx, w.o_roots), nb * g.n_layers * 32, out_kind,
+                       ctx->stream));
+    CU(cudaMemcpyAsync(last_poly_out + (b0 << g.log_last), at<QM31>(ctx, w.o_last), (nb * sizeof(QM31)) << g.log_last,
+                       out_kind, ctx->stream));
+    if (!device_io) {
+      int err_flag = 0;
+      CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, w.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+    }
+    ctx->last = w;
+    ctx->have_last = true;
+    ctx->last_nonces.clear();
+  }
+  return FRIEDA_OK;
+}
+
+// ---- prove -------------------------------------------------------------------------------
+int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride, size_t n, const uint64_t *seeds,
+               const frieda_pcs_config *cfg, uint8_t *roots_out, frieda_proof **proofs_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if ((!blobs && len) || !cfg || !proofs_out) return ctx->fail_arg("null pointer");
+  if (n == 0) return FRIEDA_OK;
+  if (n > 1 && stride < len) return ctx->fail_arg("blob_stride smaller than blob_len");
+  if (cfg->n_queries == 0) return ctx->fail_arg("reference never returns for n_queries == 0", FRIEDA_ERR_PANIC);
+  if (cfg->n_queries > 4096) return ctx->fail_arg("n_queries > 4096 is not supported");
+  if (cfg->pow_bits > 40) return ctx->fail_arg("pow_bits > 40 is not supported");
+  CU(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < n; i++) proofs_out[i] = nullptr;
+  Plan pl;
+  int rc = make_geom_fri(ctx, len, cfg, pl.g);
+  if (rc) return rc;
+  pl.fri = true;
+  pl.prove = true;
+  pl.keep = true;
+  const uint32_t nq = (uint32_t)cfg->n_queries;
+  if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
+  size_t B = pick_wave(ctx, pl, n, true, nq);
+  if ((rc = ensure_arena(ctx, pl.total))) return rc;
+  const Geom &g = pl.g;
+  const uint32_t L = g.n_layers;
+  std::vector<uint8_t> h_roots, h_fri, h_hash;
+  std::vector<frieda_qm31> h_last, h_evals;
+  std::vector<uint32_t> h_counts, h_nuniq;
+  std::vector<unsigned long long> h_offsets, h_best;
+  for (size_t b0 = 0; b0 < n; b0 += B) {
+    size_t nb = std::min(B, n - b0);
+    Plan w = pl;
+    w.B = nb;
+    const uint8_t *d_in;
+    size_t d_stride;
+    const uint64_t *d_seeds = nullptr;
+    if ((rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
+    if (seeds) {
+      CU(cudaMemcpyAsync(at<uint64_t>(ctx, w.o_seeds), seeds + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+      d_seeds = at<uint64_t>(ctx, w.o_seeds);
+    }
+    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds))) return rc;
+    // proof of work (src/proof.rs:58): rounds of 2^22 nonces until every blob has its minimum
+    Channel *chan = at<Channel>(ctx, w.o_chan);
+    unsigned long long *best = at<unsigned long long>(ctx, w.o_best);
+    CU(cudaMemsetAsync(best, 0xff, nb * 8, ctx->stream));
+    uint32_t range_log = cfg->pow_bits + 2;
+    if (range_log < 14) range_log = 14;
+    if (range_log > 24) range_log = 24;
+    for (uint64_t base = 0;; base += (uint64_t)1 << range_log) {
+      KL("grind", launch_grind(ctx->stream, chan, cfg->pow_bits, base, range_log, best, nb), 1);
+      uint32_t unsolved = 0;
+      KL("count_unsolved", launch_count_unsolved(ctx->stream, best, nb, at<uint32_t>(ctx, w.o_unsolved)), 1);
+      CU(cudaMemcpyAsync(&unsolved, at<uint32_t>(ctx, w.o_unsolved), 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (!unsolved) break;
+      if (base >> 46) return ctx->fail_arg("proof of work search exhausted");
+    }
+    // queries + decommitment (src/proof.rs:59-66)
+    uint32_t *queries = at<uint32_t>(ctx, w.o_queries);
+    uint32_t *nuniq = at<uint32_t>(ctx, w.o_nuniq);
+    KL("queries", launch_queries(ctx->stream, chan, best, g.D, nq, queries, nuniq, nb), 1);
+    DecommitParams dp;
+    std::memset(&dp, 0, sizeof dp);
+    dp.queries = queries;
+    dp.n_unique = nuniq;
+    dp.n_queries = nq;
+    dp.n_layers = L;
+    dp.D = g.D;
+    for (uint32_t l = 0; l < L; l++) {
+      dp.cols[l] = at<uint32_t>(ctx, w.o_cols[l]);
+      dp.cols_stride[l] = w.cols_stride[l];
+      dp.tree[l] = at<uint8_t>(ctx, w.o_tree[l]);
+      dp.tree_stride[l] = w.tree_stride[l];
+    }
+    dp.counts = at<uint32_t>(ctx, w.o_counts);
+    dp.offsets = at<unsigned long long>(ctx, w.o_offsets);
+    dp.evals_out = at<QM31>(ctx, w.o_evals);
+    unsigned long long *d_totals = at<unsigned long long>(ctx, w.o_totals);
+    KL("decommit_count", launch_decommit_count(ctx->stream, dp, nb), 1);
+    KL("decommit_scan", launch_decommit_scan(ctx->stream, dp, nb, d_totals), 1);
+    unsigned long long totals[2] = {0, 0};
+    CU(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // gathered witnesses live in a separate allocation sized by the exact totals
+    uint8_t *d_gather = nullptr;
+    size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
+    CU(cudaMalloc(&d_gather, align_up(fri_bytes, 256) + hash_bytes + 256));
+    dp.fri_out = reinterpret_cast<QM31 *>(d_gather);
+    dp.hash_out = d_gather + align_up(fri_bytes, 256);
+    ctx->prof_begin("decommit_write");
+    cudaError_t le = launch_decommit_write(ctx->stream, dp, nb);
+    ctx->prof_end();
+    if (le != cudaSuccess) {
+      cudaFree(d_gather);
+      return ctx->fail(le, "launch_decommit_write", __LINE__);
+    }
+    ctx->launches += 2;
+    h_roots.resize(nb * L * 32);
+    h_last.resize(nb << g.log_last);
+    h_evals.resize(nb * nq);
+    h_counts.resize(nb * L * 2);
+    h_offsets.resize(nb * L * 2);
+    h_nuniq.resize(nb);
+    h_best.resize(nb);
+    h_fri.resize(fri_bytes);
+    h_hash.resize(hash_bytes);
+    int err_flag = 0;
+    cudaError_t ce = cudaSuccess;
+    auto cp = [&](void *dst, const void *src, size_t bytes) {
+      if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    };
+    cp(h_roots.data(), at<uint8_t>(ctx, w.o_roots), h_roots.size());
+    cp(h_last.data(), at<QM31>(ctx, w.o_last), h_last.size() * sizeof(frieda_qm31));
+    cp(h_evals.data(), dp.evals_out, h_evals.size() * sizeof(frieda_qm31));
+    cp(h_counts.data(), dp.counts, h_counts.size() * 4);
+    cp(h_offsets.data(), dp.offsets, h_offsets.size() * 8);
+    cp(h_nuniq.data(), nuniq, nb * 4);
+    cp(h_best.data(), best, nb * 8);
+    cp(h_fri.data(), dp.fri_out, fri_bytes);
+    cp(h_hash.data(), dp.hash_out, hash_bytes);
+    cp(&err_flag, at<int>(ctx, w.o_err), sizeof(int));
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_gather);
+    if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
+    if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+    // assemble Proof objects (src/proof.rs:67-76)
+    for (size_t b = 0; b < nb; b++) {
+      frieda_proof *pr = (frieda_proof *)std::calloc(1, sizeof(frieda_proof));
+      if (!pr) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+      proofs_out[b0 + b] = pr;
+      pr->pcs_config = *cfg;
+      pr->log_size_bound = g.p;
+      pr->proof_of_work = h_best[b];
+      pr->n_inner_layers = g.n_inner;
+      pr->inner_layers = (frieda_layer_proof *)std::calloc(g.n_inner ? g.n_inner : 1, sizeof(frieda_layer_proof));
+      pr->n_last_layer_poly = 1u << g.log_last;
+      pr->last_layer_poly = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) << g.log_last);
+      pr->n_evaluations = h_nuniq[b];
+      pr->evaluations = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (h_nuniq[b] ? h_nuniq[b] : 1));
+      if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations)
+        return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+      std::memcpy(pr->last_layer_poly, &h_last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
+      std::memcpy(pr->evaluations, &h_evals[b * nq], sizeof(frieda_qm31) * h_nuniq[b]);
+      for (uint32_t l = 0; l < L; l++) {
+        frieda_layer_proof *lp = l == 0 ? &pr->first_layer : &pr->inner_layers[l - 1];
+        size_t ci = (b * L + l) * 2;
+        std::memcpy(lp->commitment, &h_roots[(b * L + l) * 32], 32);
+        lp->n_fri_witness = h_counts[ci];
+        lp->n_hash_witness = h_counts[ci + 1];
+        lp->n_column_witness = 0;
+        lp->fri_witness = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (lp->n_fri_witness ? lp->n_fri_witness : 1));
+        lp->hash_witness = (uint8_t *)std::malloc(32 * (size_t)(lp->n_hash_witness ? lp->n_hash_witness : 1));
+        lp->column_witness = (uint32_t *)std::malloc(4);
+        if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness)
+          return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+        std::memcpy(lp->fri_witness, h_fri.data() + h_offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
+        std::memcpy(lp->hash_witness, h_hash.data() + h_offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
+      }
+      if (roots_out) std::memcpy(roots_out + (b0 + b) * 32, &h_roots[b * L * 32], 32);
+    }
+    ctx->last = w;
+    ctx->have_last = true;
+    ctx->last_nonces.assign(h_best.begin(), h_best.end());
+  }
+  return FRIEDA_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int frieda_ctx_create(int device, frieda_ctx **out) {
+  if (!out) return FRIEDA_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return FRIEDA_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return FRIEDA_ERR_ARG;
+  }
+  frieda_ctx *ctx = new (std::nothrow) frieda_ctx();
+  if (!ctx) return FRIEDA_ERR_ALLOC;
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_scratch, 4096)) != cudaSuccess) {
+    g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    delete ctx;
+    return FRIEDA_ERR_CUDA;
+  }
+  CPoint cur = {host::GEN_X, host::GEN_Y};
+  for (int j = 0; j < 31; j++) {
+    ctx->gp.g[j] = cur;
+    cur = cpoint_add(cur, cur);
+  }
+  *out = ctx;
+  return FRIEDA_OK;
+}
+
+void frieda_ctx_destroy(frieda_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_tw);
+  cudaFree(ctx->d_itw);
+  cudaFree(ctx->arena);
+  cudaFree(ctx->d_scratch);
+  for (auto &r : ctx->prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *frieda_last_error(const frieda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int frieda_ctx_set_workspace_limit(frieda_ctx *ctx, size_t bytes) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  ctx->ws_limit = bytes;
+  return FRIEDA_OK;
+}
+uint64_t frieda_ctx_launch_count(const frieda_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *frieda_ctx_stream(const frieda_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int frieda_ctx_set_debug_keep(frieda_ctx *ctx, int on) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  ctx->debug_keep = on != 0;
+  return FRIEDA_OK;
+}
+
+int frieda_ctx_set_profiling(frieda_ctx *ctx, int on) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  ctx->profiling = on != 0;
+  return FRIEDA_OK;
+}
+// Synchronises the stream, then writes one line per kernel name: "name launches total_ms\n".
+long frieda_ctx_profile_read(frieda_ctx *ctx, char *out, size_t cap, int reset) {
+  if (!ctx || !out || cap == 0) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  struct Acc {
+    const char *name;
+    unsigned long n;
+    double ms;
+  };
+  std::vector<Acc> acc;
+  for (auto &r : ctx->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+      cudaGetLastError();
+      ms = 0.f;
+    }
+    size_t i = 0;
+    for (; i < acc.size(); i++)
+      if (std::strcmp(acc[i].name, r.name) == 0) break;
+    if (i == acc.size()) acc.push_back(Acc{r.name, 0, 0.0});
+    acc[i].n += 1;
+    acc[i].ms += ms;
+  }
+  std::string text;
+  for (auto &a : acc) {
+    char line[160];
+    std::snprintf(line, sizeof line, "%s %lu %.6f\n", a.name, a.n, a.ms);
+    text += line;
+  }
+  if (reset) {
+    for (auto &r : ctx->prof_recs) {
+      ctx->prof_pool.push_back(r.a);
+      ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+  }
+  if (text.size() + 1 > cap) return ctx->fail_arg("profile buffer too small");
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  return (long)text.size();
+}
+
+int frieda_commit(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint8_t root_out[32]) {
+  return commit_impl(ctx, data, len, len, 1, log_blowup, root_out, false);
+}
+int frieda_commit_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride, size_t n,
+                        uint32_t log_blowup, uint8_t *roots_out) {
+  return commit_impl(ctx, blobs, blob_len, blob_stride, n, log_blowup, roots_out, false);
+}
+int frieda_commit_batch_device(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride, size_t n,
+                               uint32_t log_blowup, uint8_t *d_roots_out) {
+  return commit_impl(ctx, d_blobs, blob_len, blob_stride, n, log_blowup, d_roots_out, true);
+}
+
+int frieda_fri_n_inner_layers(size_t blob_len, const frieda_pcs_config *cfg) {
+  if (!cfg) return FRIEDA_ERR_ARG;
+  frieda_ctx tmp;
+  Geom g;
+  int rc = make_geom_fri(&tmp, blob_len, cfg, g);
+  return rc ? rc : (int)g.n_inner;
+}
+int frieda_fri_commit_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride, size_t n,
+                            const uint64_t *seeds, const frieda_pcs_config *cfg, uint8_t *layer_roots_out,
+                            frieda_qm31 *last_poly_out) {
+  return fri_commit_impl(ctx, blobs, blob_len, blob_stride, n, seeds, cfg, layer_roots_out, last_poly_out, false);
+}
+int frieda_fri_commit_batch_device(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride,
+                                   size_t n, const uint64_t *d_seeds, const frieda_pcs_config *cfg,
+                                   uint8_t *d_layer_roots_out, frieda_qm31 *d_last_poly_out) {
+  return fri_commit_impl(ctx, d_blobs, blob_len, blob_stride, n, d_seeds, cfg, d_layer_roots_out, d_last_poly_out,
+                         true);
+}
+
+int frieda_prove(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                 const frieda_pcs_config *cfg, uint8_t root_out[32], frieda_proof **proof_out) {
+  return frieda_prove_batch(ctx, data, len, len, 1, seed_or_null, cfg, root_out, proof_out);
+}
+int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride, size_t n,
+                       const uint64_t *seeds, const frieda_pcs_config *cfg, uint8_t *roots_out,
+                       frieda_proof **proofs_out) {
+  int rc = prove_impl(ctx, blobs, blob_len, blob_stride, n, seeds, cfg, roots_out, proofs_out);
+  if (rc && proofs_out)
+    for (size_t i = 0; i < n; i++) {
+      frieda_proof_free(proofs_out[i]);
+      proofs_out[i] = nullptr;
+    }
+  return rc;
+}
+
+// ---- split blob (config 5) ------------------------------------------------------------------
+int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
+                              uint32_t world, uint8_t *d_subroot_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  (void)data; (void)len; (void)log_blowup; (void)rank; (void)world; (void)d_subroot_out;
+  return ctx->fail_arg("frieda_commit_split_local: not implemented yet");
+}
+int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  (void)d_subroots; (void)world; (void)root_out;
+  return ctx->fail_arg("frieda_merkle_combine: not implemented yet");
+}
+
+// ---- standalone passes ------------------------------------------------------------------------
+int frieda_pass_pack(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride, size_t n,
+                     uint32_t *d_coeffs) {
+  if (!ctx || !d_coeffs) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  Geom g;
+  g.len = blob_len;
+  g.n_felts = (uint32_t)((blob_len * 8 + 29) / 30);
+  uint32_t lg = g.n_felts ? host::ceil_log2(g.n_felts) : 0;
+  if (lg < 2) lg = 2;
+  g.p = lg - 2;
+  KL("pack", launch_pack(ctx->stream, d_blobs, blob_len, blob_stride, n, g.n_felts, g.p, d_coeffs), 1);
+  return FRIEDA_OK;
+}
+int frieda_pass_lde(frieda_ctx *ctx, const uint32_t *d_coeffs, uint32_t poly_log, uint32_t log_blowup, size_t n,
+                    uint32_t n_felts, uint32_t *d_evals) {
+  if (!ctx || !d_coeffs || !d_evals) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  uint32_t D = poly_log + log_blowup;
+  if (D == 0 || D > 28) return ctx->fail_arg("bad domain size");
+  int rc;
+  if (D >= 3 && (rc = ensure_twiddles(ctx, D - 1))) return rc;
+  Geom g;
+  g.D = D;
+  KL("lde", launch_lde(ctx->stream, d_coeffs, d_evals, poly_log, log_blowup, n, n_felts, table(ctx), half_initial_point(g)),
+     1);
+  return FRIEDA_OK;
+}
+int frieda_pass_merkle(frieda_ctx *ctx, const uint32_t *d_cols, uint32_t log, size_t n, uint8_t *d_tree,
+                       uint8_t *d_roots) {
+  if (!ctx || !d_cols || !d_roots) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (log > 28) return ctx->fail_arg("bad tree size");
+  const bool keep = d_tree != nullptr;
+  size_t slots = tree_slots(log, keep);
+  uint8_t *tree = d_tree;
+  if (!keep) {
+    int rc = ensure_arena(ctx, n * slots * 32 + 256);
+    if (rc) return rc;
+    ctx->have_last = false;
+    tree = ctx->arena;
+  }
+  MerkleBottomParams mp;
+  std::memset(&mp, 0, sizeof mp);
+  mp.src_cols = d_cols;
+  mp.src_stride = (size_t)4 << log;
+  mp.tree = tree;
+  mp.tree_stride = slots;
+  mp.log = log;
+  mp.chunk_log = log < 10 ? log : 10;
+  mp.levels = mp.chunk_log;
+  mp.src_level = log;
+  mp.write_all = keep;
+  KL("merkle_bottom_cols", launch_merkle_bottom(ctx->stream, SRC_COLS, mp, n), 1);
+  uint32_t u = log - mp.chunk_log;
+  while (u > 10) {
+    MerkleBottomParams mm = mp;
+    mm.src_cols = nullptr;
+    mm.log = u;
+    mm.src_level = u;
+    mm.chunk_log = (u - 10) < 10 ? u - 10 : 10;
+    mm.levels = mm.chunk_log;
+    KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, n), 1);
+    u -= mm.chunk_log;
+  }
+  // roots land in an aligned staging area first (caller pointers may be unaligned)
+  KL("merkle_top", launch_merkle_top(ctx->stream, tree, slots, u, keep, nullptr, 0, nullptr, nullptr, 0, n), 1);
+  CU(cudaMemcpy2DAsync(d_roots, 32, tree + 32, slots * 32, 32, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return FRIEDA_OK;
+}
+int frieda_pass_fold(frieda_ctx *ctx, const uint32_t *d_src, uint32_t log, int is_circle, size_t n,
+                     const frieda_qm31 *d_alpha, uint32_t *d_dst) {
+  if (!ctx || !d_src || !d_alpha || !d_dst) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (log < (is_circle ? 3u : 1u) || log > 28) return ctx->fail_arg("bad layer size");
+  int rc = ensure_twiddles(ctx, is_circle ? log - 1 : (log < 2 ? 1 : log));
+  if (rc) return rc;
+  KL("fold", launch_fold(ctx->stream, d_src, (size_t)4 << log, log, is_circle, reinterpret_cast<const QM31 *>(d_alpha), 1,
+                 table(ctx), d_dst, (size_t)4 << (log - 1), n),
+     1);
+  return FRIEDA_OK;
+}
+int frieda_twiddles(frieda_ctx *ctx, uint32_t k, uint32_t *tw_out, uint32_t *itw_out) {
+  if (!ctx || !tw_out || !itw_out) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (k > 27) return ctx->fail_arg("twiddle tree too large");
+  int rc = ensure_twiddles(ctx, k);
+  if (rc) return rc;
+  // the tree of half_odds(k) is the tail of the cached (possibly larger) tree
+  size_t len = (size_t)1 << k, off = ((size_t)1 << ctx->tw_K) - len;
+  CU(cudaMemcpyAsync(tw_out, ctx->d_tw + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(itw_out, ctx->d_itw + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return FRIEDA_OK;
+}
+
+long frieda_debug_fetch(frieda_ctx *ctx, int what, size_t blob, uint32_t layer, uint32_t level, void *out,
+                        size_t cap) {
+  if (!ctx || !out) return FRIEDA_ERR_ARG;
+  if (!ctx->have_last) return ctx->fail_arg("no resident wave to inspect");
+  const Plan &w = ctx->last;
+  const Geom &g = w.g;
+  if (blob >= w.B) return ctx->fail_arg("blob index outside the last wave");
+  const uint8_t *src = nullptr;
+  size_t bytes = 0;
+  switch (what) {
+    case 0:
+      src = ctx->arena + w.o_coef + blob * ((size_t)16 << g.p);
+      bytes = (size_t)16 << g.p;
+      break;
+    case 1:
+      if (layer > g.n_layers) return ctx->fail_arg("bad layer");
+      src = ctx->arena + w.o_cols[layer] + blob * w.cols_stride[layer] * 4;
+      bytes = w.cols_stride[layer] * 4;
+      break;
+    case 2: {
+      if (layer >= g.n_layers || !w.keep) return ctx->fail_arg("tree not kept");
+      uint32_t d = layer_log(g, layer);
+      if (level > d) return ctx->fail_arg("bad level");
+      src = ctx->arena + w.o_tree[layer] + (blob * w.tree_stride[layer] + ((size_t)1 << level)) * 32;
+      bytes = (size_t)32 << level;
+      break;
+    }
+    case 3:
+      if (layer >= g.n_layers) return ctx->fail_arg("bad layer");
+      src = ctx->arena + w.o_alpha + (blob * g.n_layers + layer) * sizeof(QM31);
+      bytes = sizeof(QM31);
+      break;
+    case 4:
+      src = ctx->arena + w.o_chan + blob * sizeof(Channel);
+      bytes = 32;
+      break;
+    case 5:
+      if (!w.prove) return ctx->fail_arg("no proof in the last wave");
+      src = ctx->arena + w.o_best + blob * 8;
+      bytes = 8;
+      break;
+    case 6: {
+      if (!w.prove) return ctx->fail_arg("no proof in the last wave");
+      uint32_t nu = 0;
+      CU(cudaMemcpyAsync(&nu, ctx->arena + w.o_nuniq + blob * 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      src = ctx->arena + w.o_queries + blob * (size_t)w.nq * 4;
+      bytes = (size_t)nu * 4;
+      break;
+    }
+    default:
+      return ctx->fail_arg("unknown debug selector");
+  }
+  if (bytes > cap) return ctx->fail_arg("output buffer too small");
+  CU(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return (long)bytes;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// kernels.cuh -- launcher declarations shared by the CUDA translation units and ctx.cu.
+//
+// HBM layouts (all per blob, blobs concatenated with the given strides):
+//   coefficients : 4 columns x 2^poly_log u32           (polynomial_from_bytes, src/utils.rs:21-33)
+//   layer columns: 4 columns x 2^log u32, SoA by coordinate, bit-reversed domain order
+//                  (SecureEvaluation / LineEvaluation columns, src/proof.rs:48-52)
+//   Merkle tree  : heap order, node (level k, index i) in 32-byte slot 2^k + i (slot 0 unused);
+//                  truncated trees keep only slots below 2^(top_level+1)
+//   channel      : one frieda::Channel (digest words + n_sent) per blob
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "blake2s.cuh"
+#include "m31.cuh"
+
+namespace frieda {
+
+// Twiddle tree of Coset::half_odds(K), anchored from its end: the block of length s
+// (line layer with s twiddles) starts at tw + (2^K - 2 s).  One table serves every
+// smaller domain (half_odds(k).double() == half_odds(k-1)).
+struct TwiddleTable {
+  const uint32_t *tw;   // forward, 2^K
+  const uint32_t *itw;  // element-wise inverses
+  uint32_t K;
+  FR_HD const uint32_t *blk(uint32_t s) const { return tw + (((size_t)1 << K) - 2 * (size_t)s); }
+  FR_HD const uint32_t *iblk(uint32_t s) const { return itw + (((size_t)1 << K) - 2 * (size_t)s); }
+};
+
+struct GenPowers {
+  CPoint g[31];  // G^(2^j)
+};
+
+enum MerkleSrc : int { SRC_COLS = 0, SRC_FOLD_CIRCLE = 1, SRC_FOLD_LINE = 2, SRC_NODES = 3 };
+
+struct MerkleBottomParams {
+  const uint32_t *src_cols;  // SRC_COLS: this layer; SRC_FOLD_*: previous layer (2^(log+1) per column)
+  uint32_t *dst_cols;        // SRC_FOLD_*: this layer's columns (written)
+  uint8_t *tree;             // this layer's tree
+  const QM31 *alpha;         // SRC_FOLD_*: alpha per blob
+  const uint32_t *itw_blk;   // SRC_FOLD_*: inverse twiddle block for the fold
+  size_t src_stride;         // u32 elements between blobs in src_cols
+  size_t dst_stride;         // u32 elements between blobs in dst_cols
+  size_t tree_stride;        // 32-byte slots between blobs in tree
+  size_t alpha_stride;       // QM31 elements between blobs in alpha
+  uint32_t log;              // leaf count of this pass = 2^log (SRC_NODES: node count at src_level)
+  uint32_t chunk_log;        // leaves handled per CTA
+  uint32_t levels;           // levels reduced inside the CTA (<= chunk_log)
+  uint32_t src_level;        // SRC_NODES: tree level the 2^log input nodes live on; others: == log
+  int write_all;             // write every level (leaves included) to the tree, not only the tops
+};
+
+cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
+                        uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
+cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw);
+// Circle-FFT low-degree extension of n_blobs x 4 coefficient columns.
+cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t poly_log, uint32_t log_blowup,
+                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial);
+cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomParams &p, size_t n_blobs);
+// One CTA per blob: reduce 2^top_log nodes at tree level top_log to the root; optionally
+// mix_root + draw the folding alpha on the blob's channel.
+cudaError_t launch_merkle_top(cudaStream_t st, uint8_t *tree, size_t tree_stride, uint32_t top_log, int write_all,
+                              uint8_t *roots, size_t roots_stride, Channel *chan, QM31 *alpha, size_t alpha_stride,
+                              size_t n_blobs);
+cudaError_t launch_channel_init(cudaStream_t st, Channel *chan, const uint64_t *seeds, size_t n_blobs);
+cudaError_t launch_fold(cudaStream_t st, const uint32_t *src, size_t src_stride, uint32_t src_log, int is_circle,
+                        const QM31 *alpha, size_t alpha_stride, const TwiddleTable &tt, uint32_t *dst,
+                        size_t dst_stride, size_t n_blobs);
+
+struct TailParams {
+  // layer `start_layer` (log = start_log) is resident in cols[start_layer]; the tail commits it,
+  // folds on, and finishes the FRI commit phase inside one CTA per blob.
+  uint32_t *cols[32];   // per layer: columns base (blob stride cols_stride[layer])
+  size_t cols_stride[32];
+  uint8_t *tree[32];    // per layer tree base
+  size_t tree_stride[32];
+  int write_all;
+  uint32_t start_layer, start_log;
+  uint32_t last_log;    // log size of the last (uncommitted) evaluation = log_last + log_blowup
+  uint32_t log_last;    // log of the last-layer degree bound
+  uint32_t inv_last_n;  // (2^last_log)^-1 mod P
+  uint8_t *roots;       // [blob][n_layers][32]
+  size_t roots_stride;  // bytes between blobs
+  Channel *chan;
+  QM31 *alpha;          // [blob][layer]
+  size_t alpha_stride;
+  QM31 *last_poly;      // [blob][2^log_last]
+  int *error_flag;      // set to 1 on "invalid degree"
+  TwiddleTable tt;
+};
+constexpr uint32_t TAIL_LOG = 9;      // layers with log <= TAIL_LOG are finished by the tail kernel
+constexpr uint32_t TAIL_LAST_MAX = 9; // largest supported log_last + log_blowup
+cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs);
+
+// Proof of work: best[b] = min nonce in [base, base + 2^range_log) whose raw-compress mix has
+// >= pow_bits trailing zeros, if any (atomicMin; initialise to ~0ull).
+cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t base, uint32_t range_log,
+                         unsigned long long *best, size_t n_blobs);
+cudaError_t launch_count_unsolved(cudaStream_t st, const unsigned long long *best, size_t n_blobs, uint32_t *count);
+// mix_u64(nonce) then Queries::generate: sorted unique positions per blob.
+cudaError_t launch_queries(cudaStream_t st, Channel *chan, const unsigned long long *nonce, uint32_t log_domain,
+                           uint32_t n_queries, uint32_t *queries, uint32_t *n_unique, size_t n_blobs);
+
+struct DecommitParams {
+  const uint32_t *queries;  // [blob][n_queries] sorted unique
+  const uint32_t *n_unique; // [blob]
+  uint32_t n_queries;       // stride of queries
+  uint32_t n_layers;        // 1 + inner
+  uint32_t D;               // log size of layer 0
+  const uint32_t *cols[32];
+  size_t cols_stride[32];
+  const uint8_t *tree[32];
+  size_t tree_stride[32];
+  uint32_t *counts;         // [blob][n_layers][2] = (n_fri_witness, n_hash_witness)
+  unsigned long long *offsets; // [blob][n_layers][2] element offsets into fri_out / hash_out
+  QM31 *fri_out;
+  uint8_t *hash_out;
+  QM31 *evals_out;          // [blob][n_queries]
+};
+cudaError_t launch_decommit_count(cudaStream_t st, const DecommitParams &p, size_t n_blobs);
+// Exclusive scan of counts into offsets; totals[0] = fri elements, totals[1] = hashes.
+cudaError_t launch_decommit_scan(cudaStream_t st, const DecommitParams &p, size_t n_blobs, unsigned long long *totals);
+cudaError_t launch_decommit_write(cudaStream_t st, const DecommitParams &p, size_t n_blobs);
+
+}  // namespace frieda

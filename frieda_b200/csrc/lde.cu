@@ -1,0 +1,355 @@
+// lde.cu -- byte packing, twiddle tree and the circle-FFT low-degree extension.
+//
+// Replaces, for the path of src/commit.rs:12-16 and src/proof.rs:38,44-50:
+//   utils::bytes_to_felt_le / polynomial_from_bytes   (src/utils.rs:10-33)   -> pack_kernel
+//   CpuBackend::precompute_twiddles(half_odds(K))     (src/commit.rs:15)     -> twiddle_kernel
+//   SecureCirclePoly::evaluate_with_twiddles          (src/commit.rs:16)     -> lde_block_kernel
+//
+// LDE structure: coefficients are zero-padded at the high indices and the
+// circle FFT runs its largest strides first, so the first log_blowup layers only replicate the
+// coefficient vector: the extension is 2^log_blowup independent FFTs of 2^poly_log points, block
+// hb using the twiddles whose index has hb as its high bits.  Each (blob, column, block) is one
+// CTA working in shared memory; HBM sees the coefficients once (L2 for re-reads) and the
+// evaluations once.
+#include "kernels.cuh"
+
+namespace frieda {
+
+// ---------------------------------------------------------------- pack
+// Input viewed as one little-endian bit string cut into 30-bit limbs (src/utils.rs:10-19),
+// zero-padded to 4 * 2^poly_log coefficients (src/utils.rs:23-24).
+__device__ __forceinline__ uint32_t load_word_le(const uint8_t *base, size_t len, size_t w, bool aligned) {
+  size_t byte = 4 * w;
+  if (aligned && byte + 4 <= len) return *reinterpret_cast<const uint32_t *>(base + byte);
+  uint32_t v = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (byte + j < len) v |= (uint32_t)base[byte + j] << (8 * j);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ blobs, size_t len, size_t stride,
+                                                    uint32_t n_felts, uint32_t n_coef, uint32_t *__restrict__ coef) {
+  const size_t blob = blockIdx.y;
+  const uint8_t *base = blobs + blob * stride;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(base)) & 3) == 0;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_coef; k += gridDim.x * blockDim.x) {
+    uint32_t val = 0;
+    if (k < n_felts) {
+      uint64_t bit = 30ull * k;
+      size_t w = (size_t)(bit >> 5);
+      uint32_t off = (uint32_t)(bit & 31);
+      uint32_t w0 = load_word_le(base, len, w, aligned);
+      uint32_t w1 = off > 2 ? load_word_le(base, len, w + 1, aligned) : 0u;
+      val = __funnelshift_r(w0, w1, off) & 0x3fffffffu;
+    }
+    coef[blob * n_coef + k] = val;
+  }
+}
+
+cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
+                        uint32_t n_felts, uint32_t poly_log, uint32_t *coef) {
+  uint32_t n_coef = 4u << poly_log;
+  uint32_t bx = (n_coef + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  for (size_t b0 = 0; b0 < n_blobs; b0 += 65535) {
+    size_t nb = n_blobs - b0 < 65535 ? n_blobs - b0 : 65535;
+    pack_kernel<<<dim3(bx, (unsigned)nb), 256, 0, st>>>(blobs + b0 * stride, len, stride, n_felts, n_coef,
+                                                        coef + b0 * n_coef);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- twiddles
+// T (length 2^K): for level l = 0..K-1 the x-coordinates of the first half of half_odds(K-l),
+// bit-reversed; then a trailing 1 (stwo slow_precompute_twiddles).
+__device__ __forceinline__ CPoint point_from_index(const GenPowers &gp, uint32_t idx) {
+  CPoint r = {1u, 0u};
+#pragma unroll 1
+  for (int j = 0; j < 31; j++)
+    if ((idx >> j) & 1u) r = cpoint_add(r, gp.g[j]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) twiddle_kernel(const __grid_constant__ GenPowers gp, uint32_t K,
+                                                       uint32_t *__restrict__ tw, uint32_t *__restrict__ itw) {
+  size_t len = (size_t)1 << K;
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= len) return;
+  size_t rem = len - g;  // distance from the end, >= 1
+  if (rem == 1) {
+    tw[g] = 1;
+    itw[g] = 1;
+    return;
+  }
+  // the block of length s occupies [len - 2s, len - s): s = largest power of two < rem
+  uint32_t ls = 63 - __clzll((long long)(rem - 1));
+  size_t s = (size_t)1 << ls;
+  uint32_t i = (uint32_t)(g - (len - 2 * s));
+  uint32_t idx = half_odds_index(ls + 1, bit_reverse(i, ls));
+  uint32_t x = point_from_index(gp, idx).x;
+  tw[g] = x;
+  itw[g] = m31_inv(x);
+}
+
+cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw) {
+  size_t len = (size_t)1 << K;
+  unsigned blocks = (unsigned)((len + 255) / 256);
+  twiddle_kernel<<<blocks, 256, 0, st>>>(gp, K, tw, itw);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- LDE
+// One CTA = one (block hb, column, blob): 2^p-point FFT in shared memory, layers p-1 .. 0.
+// Layer i >= 1 (line): twiddle = blk(2^(K-i))[idx >> (i+1)];  layer 0 (circle): from the pairs
+// (x, y) of blk(2^(K-1)) as [y, -y, -x, x] (stwo circle_twiddles_from_line_twiddles).
+// Columns whose coefficients are all zero evaluate to zero; layers whose upper inputs are all
+// zero (coefficient prefix shorter than the stride) are replications.  Both are arithmetic
+// identities, not special-casing of a config.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *__restrict__ coef,
+                                                            uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
+                                                            uint32_t n_felts, TwiddleTable tt) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t hb = blockIdx.x, col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  const uint32_t n4 = 1u << p;
+  const uint32_t D = p + beta, K = D - 1;
+  const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
+  uint32_t *out = eval + ((blob * 4 + col) << D) + ((size_t)hb << p);
+  // non-zero prefix of this column
+  uint32_t first = col * n4;
+  uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
+  if (nz == 0) {
+    for (uint32_t i = threadIdx.x; i < n4; i += THREADS) out[i] = 0u;
+    return;
+  }
+  // m = ceil(log2(nz)): layers i >= m only replicate
+  uint32_t m = nz > 1 ? 32 - __clz(nz - 1) : 0;
+  const uint32_t mask = (1u << m) - 1;
+  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) {
+    uint32_t j = i & mask;
+    sm[i] = j < nz ? c[j] : 0u;
+  }
+  __syncthreads();
+  const uint32_t half = n4 >> 1;
+  for (int i = (int)m - 1; i >= 1; i--) {
+    const uint32_t *tw = tt.blk(1u << (K - i)) + ((size_t)hb << (p - i - 1));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
+      uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
+      uint32_t t = __ldg(tw + hi);
+      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
+      sm[a] = m31_add(va, tmp);
+      sm[b] = m31_sub(va, tmp);
+    }
+    __syncthreads();
+  }
+  if (m >= 1) {
+    // circle layer; results go straight to HBM
+    const uint32_t *tw = tt.blk(1u << (K - 1));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t h = (hb << (p - 1)) | bf;
+      uint32_t q = h >> 2, e = h & 3;
+      uint32_t x = __ldg(tw + 2 * q), y = __ldg(tw + 2 * q + 1);
+      uint32_t t = e == 0 ? y : e == 1 ? m31_neg(y) : e == 2 ? m31_neg(x) : x;
+      uint2 v = reinterpret_cast<const uint2 *>(sm)[bf];
+      uint32_t tmp = m31_mul(v.y, t);
+      uint2 r = {m31_add(v.x, tmp), m31_sub(v.x, tmp)};
+      reinterpret_cast<uint2 *>(out)[bf] = r;
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < n4; i += THREADS) out[i] = sm[i];
+  }
+}
+
+// D == 1 and D == 2: stwo hard-codes these; one thread per (blob, column).
+__global__ void lde_tiny_kernel(const uint32_t *__restrict__ coef, uint32_t *__restrict__ eval, uint32_t p,
+                                uint32_t D, size_t n_cols, CPoint init) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_cols) return;
+  const uint32_t *c = coef + (g << p);
+  uint32_t *o = eval + (g << D);
+  uint32_t v[4] = {0, 0, 0, 0};
+  for (uint32_t i = 0; i < (1u << p); i++) v[i] = c[i];
+  auto bfly = [](uint32_t &a, uint32_t &b, uint32_t t) {
+    uint32_t tmp = m31_mul(b, t), va = a;
+    a = m31_add(va, tmp);
+    b = m31_sub(va, tmp);
+  };
+  if (D == 1) {
+    bfly(v[0], v[1], init.y);
+  } else {
+    bfly(v[0], v[2], init.x);
+    bfly(v[1], v[3], init.x);
+    bfly(v[0], v[1], init.y);
+    bfly(v[2], v[3], m31_neg(init.y));
+  }
+  for (uint32_t i = 0; i < (1u << D); i++) o[i] = v[i];
+}
+
+// Large polynomials (2^p points do not fit one CTA's shared memory): the top r layers are done
+// on strided tiles -- 2^r rows that are 2^(p-r) apart, 2^w consecutive columns each -- so that
+// every global access is a contiguous 2^w-word segment; the remaining layers run per
+// contiguous chunk.  FIRST reads the replicated coefficients (index mod 2^p), later passes work
+// in place on the evaluations.
+template <int THREADS, bool FIRST>
+__global__ void __launch_bounds__(THREADS) lde_strided_kernel(const uint32_t *__restrict__ coef,
+                                                              uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
+                                                              uint32_t n_felts, uint32_t top, uint32_t r, uint32_t w,
+                                                              TwiddleTable tt) {
+  // handles layers top-1 .. top-r of every 2^top-point sub-FFT; rows are 2^(top-r) apart
+  extern __shared__ uint32_t sm[];
+  const uint32_t D = p + beta, K = D - 1;
+  const uint32_t col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  const uint32_t row_stride_log = top - r;                 // distance between rows (log)
+  const uint32_t tiles_per_sub = 1u << (row_stride_log - w);  // tiles inside one sub-FFT
+  const uint32_t sub = blockIdx.x / tiles_per_sub;         // which 2^top-point sub-FFT (global index)
+  const uint32_t tile = blockIdx.x % tiles_per_sub;
+  const size_t base = ((size_t)sub << top) + ((size_t)tile << w);
+  const uint32_t n4 = 1u << p;
+  uint32_t *ev = eval + ((blob * 4 + col) << D);
+  const uint32_t rows = 1u << r, cols = 1u << w;
+  uint32_t first = col * n4;
+  uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
+  if (FIRST) {
+    const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
+    for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
+      uint32_t row = e >> w, cc = e & (cols - 1);
+      size_t idx = base + ((size_t)row << row_stride_log) + cc;
+      uint32_t j = (uint32_t)(idx & (n4 - 1));
+      sm[e] = j < nz ? c[j] : 0u;
+    }
+  } else {
+    for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
+      uint32_t row = e >> w, cc = e & (cols - 1);
+      sm[e] = ev[base + ((size_t)row << row_stride_log) + cc];
+    }
+  }
+  __syncthreads();
+  const uint32_t half = (rows * cols) >> 1;
+  for (int li = (int)r - 1; li >= 0; li--) {
+    // local row bit li <-> global layer i = row_stride_log + li
+    const uint32_t i = row_stride_log + li;
+    const uint32_t *tw = tt.blk(1u << (K - i));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t cc = bf & (cols - 1), rb = bf >> w;  // rb indexes row pairs
+      uint32_t lo = rb & ((1u << li) - 1), hi = rb >> li;
+      uint32_t ra = (hi << (li + 1)) | lo, rbb = ra + (1u << li);
+      size_t ga = base + ((size_t)ra << row_stride_log) + cc;  // global index of element a
+      uint32_t t = __ldg(tw + (ga >> (i + 1)));
+      uint32_t a = (ra << w) | cc, b = (rbb << w) | cc;
+      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
+      sm[a] = m31_add(va, tmp);
+      sm[b] = m31_sub(va, tmp);
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
+    uint32_t row = e >> w, cc = e & (cols - 1);
+    ev[base + ((size_t)row << row_stride_log) + cc] = sm[e];
+  }
+}
+
+// Contiguous chunk pass, in place on the evaluations: layers c-1 .. 0 of every 2^c chunk.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) lde_chunk_kernel(uint32_t *__restrict__ eval, uint32_t D, uint32_t c,
+                                                            TwiddleTable tt) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t K = D - 1;
+  const uint32_t col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  const size_t chunk = blockIdx.x;
+  uint32_t *ev = eval + ((blob * 4 + col) << D) + (chunk << c);
+  const uint32_t n = 1u << c;
+  for (uint32_t i = threadIdx.x; i < n; i += THREADS) sm[i] = ev[i];
+  __syncthreads();
+  const uint32_t half = n >> 1;
+  for (int i = (int)c - 1; i >= 1; i--) {
+    const uint32_t *tw = tt.blk(1u << (K - i)) + (chunk << (c - i - 1));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
+      uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
+      uint32_t t = __ldg(tw + hi);
+      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
+      sm[a] = m31_add(va, tmp);
+      sm[b] = m31_sub(va, tmp);
+    }
+    __syncthreads();
+  }
+  const uint32_t *tw = tt.blk(1u << (K - 1));
+  for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+    size_t h = (chunk << (c - 1)) | bf;
+    size_t q = h >> 2;
+    uint32_t e = (uint32_t)(h & 3);
+    uint32_t x = __ldg(tw + 2 * q), y = __ldg(tw + 2 * q + 1);
+    uint32_t t = e == 0 ? y : e == 1 ? m31_neg(y) : e == 2 ? m31_neg(x) : x;
+    uint2 v = reinterpret_cast<const uint2 *>(sm)[bf];
+    uint32_t tmp = m31_mul(v.y, t);
+    uint2 rr = {m31_add(v.x, tmp), m31_sub(v.x, tmp)};
+    reinterpret_cast<uint2 *>(ev)[bf] = rr;
+  }
+}
+
+constexpr uint32_t LDE_SMEM_LOG_MAX = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
+
+cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t p, uint32_t beta,
+                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial) {
+  const uint32_t D = p + beta;
+  if (D == 0) return cudaErrorInvalidValue;
+  if (D <= 2) {
+    size_t n_cols = n_blobs * 4;
+    lde_tiny_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(coef, eval, p, D, n_cols, half_initial);
+    return cudaGetLastError();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(lde_block_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
+    cudaFuncSetAttribute(lde_block_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
+    cudaFuncSetAttribute(lde_strided_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
+    cudaFuncSetAttribute(lde_strided_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
+    cudaFuncSetAttribute(lde_chunk_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
+    attr_set = true;
+  }
+  for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
+    size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
+    const uint32_t *cf = coef + b0 * ((size_t)4 << p);
+    uint32_t *ev = eval + b0 * ((size_t)4 << D);
+    if (p <= LDE_SMEM_LOG_MAX) {
+      dim3 grid(1u << beta, 4, (unsigned)nb);
+      size_t smem = (size_t)4 << p;
+      if (p >= 11)
+        lde_block_kernel<1024><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, tt);
+      else
+        lde_block_kernel<256><<<grid, 256, smem, st>>>(cf, ev, p, beta, n_felts, tt);
+    } else {
+      // strided passes over layers p-1 .. c, then contiguous chunks of 2^c; every tile is
+      // 2^14 words (64 KiB) with rows of at least 2^5 consecutive words (128 B)
+      const uint32_t c = 14;
+      const uint32_t n_passes = (p - c + 8) / 9;
+      uint32_t top = p;
+      bool firstpass = true;
+      for (uint32_t pass = 0; pass < n_passes; pass++) {
+        uint32_t left = n_passes - pass;
+        uint32_t r = (top - c + left - 1) / left;
+        uint32_t w = 14 - r;
+        uint32_t subs = 1u << (D - top);
+        uint32_t tiles = subs << (top - r - w);
+        dim3 grid(tiles, 4, (unsigned)nb);
+        size_t smem = (size_t)4 << (r + w);
+        if (firstpass)
+          lde_strided_kernel<1024, true><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt);
+        else
+          lde_strided_kernel<1024, false><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt);
+        firstpass = false;
+        top -= r;
+      }
+      dim3 grid(1u << (D - c), 4, (unsigned)nb);
+      lde_chunk_kernel<1024><<<grid, 1024, (size_t)4 << c, st>>>(ev, D, c, tt);
+    }
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace frieda

@@ -1,0 +1,217 @@
+// merkle.cu -- Merkle commitment kernels (one BLAKE2s compression per thread, state in
+// registers, level-by-level reduction in shared memory) with the FRI fold fused in front of
+// the leaf hashing.
+//
+// Replaces MerkleProver::<CpuBackend, Blake2sMerkleHasher>::commit (src/commit.rs:17-22) and,
+// for the FRI layers, FriOps::fold_circle_into_line / fold_line followed by
+// FriInnerLayerProver::new's MerkleProver::commit (stwo fri.rs, reached from src/proof.rs:52-57).
+//
+// merkle_bottom_kernel<SRC>: each CTA owns 2^chunk_log consecutive leaves of one blob.
+//   SRC_COLS         leaf i = H(col0[i], col1[i], col2[i], col3[i])
+//   SRC_FOLD_CIRCLE  first folds the pair (2i, 2i+1) of the circle evaluation with alpha
+//                    (f0 + alpha f1, f1 = (a - b) / y), stores the new line layer, hashes it
+//   SRC_FOLD_LINE    same with the line twiddle 1/x
+//   SRC_NODES        leaves are 2^log existing nodes of tree level src_level (middle pass)
+// then reduces `levels` tree levels in shared memory and writes the surviving tops (and, when
+// write_all, every level on the way) into the heap-ordered tree.
+#include "kernels.cuh"
+
+namespace frieda {
+
+constexpr int MB_THREADS = 256;
+constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB + 16 KiB of shared memory
+
+struct alignas(16) Hash32 {
+  uint4 lo, hi;
+};
+
+__device__ __forceinline__ void store_hash(Hash32 *dst, const uint32_t h[8]) {
+  dst->lo = make_uint4(h[0], h[1], h[2], h[3]);
+  dst->hi = make_uint4(h[4], h[5], h[6], h[7]);
+}
+__device__ __forceinline__ void load_pair(const Hash32 *src, uint32_t m[16]) {
+  uint4 a = src[0].lo, b = src[0].hi, c = src[1].lo, d = src[1].hi;
+  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+  m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+  m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w;
+  m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+}
+
+// inverse twiddle of the circle->line fold for pair i: from the (x, y)
+// pairs of the largest line block as [1/y, -1/y, -1/x, 1/x].
+__device__ __forceinline__ uint32_t circle_fold_itw(const uint32_t *iblk, size_t i) {
+  size_t q = i >> 2;
+  uint32_t e = (uint32_t)(i & 3);
+  uint32_t v = __ldg(iblk + 2 * q + (e < 2 ? 1 : 0));
+  return (e == 1 || e == 2) ? m31_neg(v) : v;
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleBottomParams p) {
+  __shared__ Hash32 sm_a[1u << MB_CHUNK_LOG_MAX];
+  __shared__ Hash32 sm_b[1u << (MB_CHUNK_LOG_MAX - 1)];
+  const size_t blob = blockIdx.y;
+  const uint32_t chunk = blockIdx.x;
+  const uint32_t n_chunk = 1u << p.chunk_log;
+  const size_t leaf0 = (size_t)chunk << p.chunk_log;
+  Hash32 *tree = reinterpret_cast<Hash32 *>(p.tree) + blob * p.tree_stride;
+
+  if (SRC == SRC_NODES) {
+    const Hash32 *src = tree + ((size_t)1 << p.src_level) + leaf0;
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) sm_a[j] = src[j];
+  } else {
+    const size_t n = (size_t)1 << p.log;
+    QM31 alpha;
+    if (SRC == SRC_FOLD_CIRCLE || SRC == SRC_FOLD_LINE) alpha = p.alpha[blob * p.alpha_stride];
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
+      const size_t i = leaf0 + j;
+      uint32_t c0, c1, c2, c3;
+      if (SRC == SRC_COLS) {
+        const uint32_t *s = p.src_cols + blob * p.src_stride + i;
+        c0 = __ldg(s);
+        c1 = __ldg(s + n);
+        c2 = __ldg(s + 2 * n);
+        c3 = __ldg(s + 3 * n);
+      } else {
+        const uint2 *s = reinterpret_cast<const uint2 *>(p.src_cols + blob * p.src_stride) + i;
+        uint2 e0 = __ldg(s), e1 = __ldg(s + n), e2 = __ldg(s + 2 * n), e3 = __ldg(s + 3 * n);
+        QM31 a = {{e0.x, e1.x, e2.x, e3.x}}, b = {{e0.y, e1.y, e2.y, e3.y}};
+        uint32_t itw = SRC == SRC_FOLD_CIRCLE ? circle_fold_itw(p.itw_blk, i) : __ldg(p.itw_blk + i);
+        QM31 f = fri_fold_pair(a, b, itw, alpha);
+        c0 = f.v[0];
+        c1 = f.v[1];
+        c2 = f.v[2];
+        c3 = f.v[3];
+        uint32_t *d = p.dst_cols + blob * p.dst_stride + i;
+        d[0] = c0;
+        d[n] = c1;
+        d[2 * n] = c2;
+        d[3 * n] = c3;
+      }
+      uint32_t h[8];
+      merkle_hash_leaf(c0, c1, c2, c3, h);
+      store_hash(&sm_a[j], h);
+      if (p.write_all) store_hash(tree + n + i, h);
+    }
+  }
+  __syncthreads();
+  // level-by-level reduction, ping-pong between the two shared buffers
+  Hash32 *cur = sm_a, *nxt = sm_b;
+  uint32_t cnt = n_chunk;
+  uint32_t level = (SRC == SRC_NODES ? p.src_level : p.log);
+  size_t idx0 = leaf0;
+  for (uint32_t l = 0; l < p.levels; l++) {
+    cnt >>= 1;
+    level -= 1;
+    idx0 >>= 1;
+    const bool top = (l + 1 == p.levels);
+    for (uint32_t j = threadIdx.x; j < cnt; j += MB_THREADS) {
+      uint32_t m[16], h[8];
+      load_pair(cur + 2 * j, m);
+      merkle_hash_node(m, h);
+      store_hash(&nxt[j], h);
+      if (p.write_all || top) store_hash(tree + ((size_t)1 << level) + idx0 + j, h);
+    }
+    __syncthreads();
+    Hash32 *t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  if (p.levels == 0 && !p.write_all && SRC != SRC_NODES) {
+    // no reduction requested: the leaves themselves are the tops
+    const size_t n = (size_t)1 << p.log;
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) tree[n + leaf0 + j] = sm_a[j];
+  }
+}
+
+cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomParams &p, size_t n_blobs) {
+  if (p.chunk_log > MB_CHUNK_LOG_MAX || p.levels > p.chunk_log || p.chunk_log > p.log) return cudaErrorInvalidValue;
+  unsigned chunks = 1u << (p.log - p.chunk_log);
+  for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
+    size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
+    MerkleBottomParams q = p;
+    if (q.src_cols) q.src_cols += b0 * p.src_stride;
+    if (q.dst_cols) q.dst_cols += b0 * p.dst_stride;
+    q.tree += b0 * p.tree_stride * 32;
+    if (q.alpha) q.alpha += b0 * p.alpha_stride;
+    dim3 grid(chunks, (unsigned)nb);
+    switch (src) {
+      case SRC_COLS: merkle_bottom_kernel<SRC_COLS><<<grid, MB_THREADS, 0, st>>>(q); break;
+      case SRC_FOLD_CIRCLE: merkle_bottom_kernel<SRC_FOLD_CIRCLE><<<grid, MB_THREADS, 0, st>>>(q); break;
+      case SRC_FOLD_LINE: merkle_bottom_kernel<SRC_FOLD_LINE><<<grid, MB_THREADS, 0, st>>>(q); break;
+      case SRC_NODES: merkle_bottom_kernel<SRC_NODES><<<grid, MB_THREADS, 0, st>>>(q); break;
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- top of the tree + channel
+// One CTA per blob.  Reduces the 2^top_log nodes of level top_log to the root, stores the root,
+// then (chan != nullptr) runs the Fiat-Shamir step of FriProver::commit for this layer:
+// MC::mix_root(channel, root); folding_alpha = channel.draw_felt().
+constexpr int MT_THREADS = 128;
+constexpr uint32_t MT_TOP_LOG_MAX = 10;
+
+__global__ void __launch_bounds__(MT_THREADS) merkle_top_kernel(uint8_t *tree_, size_t tree_stride, uint32_t top_log,
+                                                                 int write_all, uint8_t *roots, size_t roots_stride,
+                                                                 Channel *chan, QM31 *alpha, size_t alpha_stride) {
+  __shared__ Hash32 sm_a[1u << MT_TOP_LOG_MAX];
+  __shared__ Hash32 sm_b[1u << (MT_TOP_LOG_MAX - 1)];
+  const size_t blob = blockIdx.x;
+  Hash32 *tree = reinterpret_cast<Hash32 *>(tree_) + blob * tree_stride;
+  uint32_t cnt = 1u << top_log;
+  for (uint32_t j = threadIdx.x; j < cnt; j += MT_THREADS) sm_a[j] = tree[cnt + j];
+  __syncthreads();
+  Hash32 *cur = sm_a, *nxt = sm_b;
+  for (uint32_t level = top_log; level > 0; level--) {
+    cnt >>= 1;
+    for (uint32_t j = threadIdx.x; j < cnt; j += MT_THREADS) {
+      uint32_t m[16], h[8];
+      load_pair(cur + 2 * j, m);
+      merkle_hash_node(m, h);
+      store_hash(&nxt[j], h);
+      if (write_all || level == 1) store_hash(tree + cnt + j, h);
+    }
+    __syncthreads();
+    Hash32 *t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  if (threadIdx.x == 0) {
+    Hash32 r = cur[0];
+    uint32_t root[8] = {r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, r.hi.z, r.hi.w};
+    if (roots) store_hash(reinterpret_cast<Hash32 *>(roots + blob * roots_stride), root);
+    if (chan) {
+      Channel c = chan[blob];
+      channel_mix_root(c, root);
+      QM31 a = channel_draw_felt(c);
+      chan[blob] = c;
+      alpha[blob * alpha_stride] = a;
+    }
+  }
+}
+
+cudaError_t launch_merkle_top(cudaStream_t st, uint8_t *tree, size_t tree_stride, uint32_t top_log, int write_all,
+                              uint8_t *roots, size_t roots_stride, Channel *chan, QM31 *alpha, size_t alpha_stride,
+                              size_t n_blobs) {
+  if (top_log > MT_TOP_LOG_MAX) return cudaErrorInvalidValue;
+  merkle_top_kernel<<<(unsigned)n_blobs, MT_THREADS, 0, st>>>(tree, tree_stride, top_log, write_all, roots,
+                                                              roots_stride, chan, alpha, alpha_stride);
+  return cudaGetLastError();
+}
+
+__global__ void channel_init_kernel(Channel *chan, const uint64_t *seeds, size_t n) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  Channel c;
+  channel_init(c);
+  if (seeds) channel_mix_u64(c, seeds[b]);  // src/proof.rs:40-42
+  chan[b] = c;
+}
+cudaError_t launch_channel_init(cudaStream_t st, Channel *chan, const uint64_t *seeds, size_t n_blobs) {
+  channel_init_kernel<<<(unsigned)((n_blobs + 127) / 128), 128, 0, st>>>(chan, seeds, n_blobs);
+  return cudaGetLastError();
+}
+
+}  // namespace frieda

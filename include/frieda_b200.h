@@ -1,0 +1,187 @@
+/*
+ * frieda_b200.h -- C ABI of libfrieda_b200.so: FRIEDA's data-parallel commit path on B200.
+ *
+ * The reference crate (keep-starknet-strange/frieda) has no FFI boundary; its contract is the
+ * Rust API at src/lib.rs:31-43 (api::commit / api::generate_proof / api::verify), forwarding to
+ * src/commit.rs:11 (commit), src/proof.rs:28,32,79 (generate_proof, commit_and_generate_proof,
+ * verify_proof) with the `Proof` struct of src/proof.rs:19-26.  Each entry point below names the
+ * reference function it replaces; INTEGRATION.md shows the `extern "C"` block and the shim
+ * `src/{commit,proof}.rs` a maintainer would add.
+ *
+ * Conventions crossing the ABI
+ *   - a commitment / Merkle hash is 32 bytes = the 8 BLAKE2s state words little-endian
+ *     (`Commitment = [u8; 32]`, src/commit.rs:9);
+ *   - a QM31 is 4 x u32 little-endian (a, b, c, d) for (a + b i) + (c + d i) u;
+ *   - inputs are borrowed for the call (`&[u8]`), roots are caller-allocated, proofs are
+ *     library-allocated and released with frieda_proof_free (mirrors `Proof` being owned);
+ *   - return 0 on success, negative FRIEDA_ERR_* otherwise.  The reference panics where
+ *     FRIEDA_ERR_PANIC is returned (src/proof.rs:61, stwo asserts); the Rust shim panics on it.
+ *   - a context owns one device, its streams, twiddle cache and workspace; calls on distinct
+ *     contexts may run concurrently, one context is not internally locked.
+ *   - there is NO CPU fallback: every compute entry point fails with FRIEDA_ERR_CUDA when no
+ *     CUDA device is usable.  frieda_verify is host-only by design (sub-millisecond).
+ */
+#ifndef FRIEDA_B200_H
+#define FRIEDA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRIEDA_OK 0
+#define FRIEDA_ERR_PANIC (-1)   /* the reference would panic on this input */
+#define FRIEDA_ERR_ALLOC (-2)   /* host or device allocation failed */
+#define FRIEDA_ERR_CUDA (-3)    /* CUDA runtime error / no device */
+#define FRIEDA_ERR_ARG (-4)     /* invalid argument (null pointer, unsupported size) */
+
+typedef struct { uint32_t v[4]; } frieda_qm31;
+
+/* stwo PcsConfig { pow_bits, fri_config: FriConfig { log_blowup_factor,
+ * log_last_layer_degree_bound, n_queries } } as built by literal in src/lib.rs:71-78,
+ * src/proof.rs:109-116, benches/proof.rs:5-12. */
+typedef struct {
+  uint32_t log_blowup_factor;
+  uint32_t log_last_layer_degree_bound;
+  uint64_t n_queries;
+  uint32_t pow_bits;
+} frieda_pcs_config;
+
+/* stwo FriLayerProof<Blake2sMerkleHasher>: fri_witness, decommitment {hash_witness,
+ * column_witness}, commitment. */
+typedef struct {
+  uint8_t commitment[32];
+  uint32_t n_fri_witness;
+  frieda_qm31 *fri_witness;
+  uint32_t n_hash_witness;
+  uint8_t *hash_witness; /* n_hash_witness * 32 bytes */
+  uint32_t n_column_witness;
+  uint32_t *column_witness; /* always empty on this path */
+} frieda_layer_proof;
+
+/* frieda::proof::Proof (src/proof.rs:19-26); `proof: FriProof` is flattened into
+ * first_layer / inner_layers / last_layer_poly. */
+typedef struct frieda_proof {
+  frieda_layer_proof first_layer;
+  uint32_t n_inner_layers;
+  frieda_layer_proof *inner_layers;
+  uint32_t n_last_layer_poly;
+  frieda_qm31 *last_layer_poly;
+  uint64_t proof_of_work;
+  frieda_pcs_config pcs_config;
+  uint32_t log_size_bound;
+  uint32_t n_evaluations;
+  frieda_qm31 *evaluations;
+} frieda_proof;
+
+typedef struct frieda_ctx frieda_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`.  FRIEDA_ERR_CUDA if there is none. */
+int frieda_ctx_create(int device, frieda_ctx **out);
+void frieda_ctx_destroy(frieda_ctx *ctx);
+/* Last error text of this context (or of the failed create when ctx is NULL). */
+const char *frieda_last_error(const frieda_ctx *ctx);
+/* Caps the device workspace a batched call may use (bytes; 0 = 80% of free memory). */
+int frieda_ctx_set_workspace_limit(frieda_ctx *ctx, size_t bytes);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t frieda_ctx_launch_count(const frieda_ctx *ctx);
+/* Per-kernel timing: when on, every launch is bracketed by CUDA events on the context's stream.
+ * frieda_ctx_profile_read synchronises and writes "name launches total_ms\n" per kernel name
+ * (returns the text length, or a negative error); reset != 0 clears the records. */
+int frieda_ctx_set_profiling(frieda_ctx *ctx, int on);
+long frieda_ctx_profile_read(frieda_ctx *ctx, char *out, size_t cap, int reset);
+/* The stream all of this context's kernels are launched on (a cudaStream_t). */
+void *frieda_ctx_stream(const frieda_ctx *ctx);
+
+/* ---- commit: replaces frieda::commit::commit (src/commit.rs:11-23) -------------------- */
+/* Host buffer in, 32-byte root out. */
+int frieda_commit(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
+                  uint8_t root_out[32]);
+/* n blobs of blob_len bytes, blob i at blobs + i*blob_stride (host memory, ideally pinned);
+ * roots_out = n * 32 bytes (host).  Host<->device copies are overlapped with compute. */
+int frieda_commit_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride,
+                        size_t n, uint32_t log_blowup, uint8_t *roots_out);
+/* Same with DEVICE pointers for input and output (inputs already resident in HBM).
+ * Asynchronous on frieda_ctx_stream(); d_roots_out = n * 32 bytes of device memory. */
+int frieda_commit_batch_device(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride,
+                               size_t n, uint32_t log_blowup, uint8_t *d_roots_out);
+
+/* ---- FRI commit phase: the `FriProver::commit` call inside commit_and_generate_proof
+ *      (src/proof.rs:38-57): channel init (+ optional mix_u64(seed)), LDE, first-layer tree,
+ *      circle->line fold, inner layers with their Merkle commitments, last-layer polynomial.
+ *      Outputs per blob: (1 + n_inner) layer roots (layer 0 == commit() root) and the
+ *      2^log_last last-layer coefficients.  seeds may be NULL (no seed for any blob). ------ */
+/* Number of inner FRI layers for a blob of blob_len bytes under cfg (or negative error). */
+int frieda_fri_n_inner_layers(size_t blob_len, const frieda_pcs_config *cfg);
+int frieda_fri_commit_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride, size_t n,
+                            const uint64_t *seeds, const frieda_pcs_config *cfg, uint8_t *layer_roots_out,
+                            frieda_qm31 *last_poly_out);
+int frieda_fri_commit_batch_device(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride,
+                                   size_t n, const uint64_t *d_seeds, const frieda_pcs_config *cfg,
+                                   uint8_t *d_layer_roots_out, frieda_qm31 *d_last_poly_out);
+
+/* ---- proof generation: replaces commit_and_generate_proof (src/proof.rs:32-77);
+ *      generate_proof (src/proof.rs:28-30) is the same call ignoring root_out. ------------- */
+int frieda_prove(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                 const frieda_pcs_config *cfg, uint8_t root_out[32], frieda_proof **proof_out);
+/* seeds: n values or NULL; roots_out: n*32 bytes or NULL; proofs_out: n pointers. */
+int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, size_t blob_stride, size_t n,
+                       const uint64_t *seeds, const frieda_pcs_config *cfg, uint8_t *roots_out,
+                       frieda_proof **proofs_out);
+
+/* ---- verification: replaces verify_proof (src/proof.rs:79-101).  Host only.
+ *      Returns 1 (valid), 0 (invalid) or FRIEDA_ERR_PANIC where the reference panics
+ *      (too few `evaluations`, src/proof.rs:166-173). */
+int frieda_verify(const frieda_proof *proof, const uint64_t *seed_or_null);
+
+/* ---- proof objects --------------------------------------------------------------------- */
+void frieda_proof_free(frieda_proof *proof);
+frieda_proof *frieda_proof_clone(const frieda_proof *proof);
+/* Flat little-endian encoding (the reference picks no wire format).
+ * Returns the byte count; writes only if cap is large enough. */
+size_t frieda_proof_serialize(const frieda_proof *proof, uint8_t *out, size_t cap);
+int frieda_proof_deserialize(const uint8_t *bytes, size_t len, frieda_proof **proof_out);
+
+/* ---- one oversized blob split across GPUs (BASELINE config 5) -------------------------
+ * Rank `rank` of `world` (a power of two) computes the LDE of its contiguous bit-reversed
+ * index range [rank*N/world, (rank+1)*N/world) from the whole input and the root of the
+ * Merkle subtree over it.  d_subroot_out: 32 bytes of device memory (the all-gather input). */
+int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
+                              uint32_t rank, uint32_t world, uint8_t *d_subroot_out);
+/* Hashes the top log2(world) Merkle levels over the gathered subtree roots
+ * (d_subroots = world * 32 bytes of device memory, rank order) into root_out (host). */
+int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]);
+
+/* ---- standalone passes (bench.py's per-pass roofline; tests).  Device pointers. --------
+ * LDE: d_coeffs = n * 4 * 2^poly_log u32 -> d_evals = n * 4 * 2^(poly_log+log_blowup) u32. */
+int frieda_pass_pack(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride, size_t n,
+                     uint32_t *d_coeffs);
+int frieda_pass_lde(frieda_ctx *ctx, const uint32_t *d_coeffs, uint32_t poly_log, uint32_t log_blowup, size_t n,
+                    uint32_t n_felts, uint32_t *d_evals);
+/* Merkle tree over 4 columns of 2^log each: d_tree = n * 2^(log+1) * 32 bytes, node (level k,
+ * index i) at slot 2^k + i (slot 0 unused); pass d_tree = NULL to keep only roots.
+ * d_roots = n * 32 bytes. */
+int frieda_pass_merkle(frieda_ctx *ctx, const uint32_t *d_cols, uint32_t log, size_t n, uint8_t *d_tree,
+                       uint8_t *d_roots);
+/* FRI folds without hashing: circle (is_circle=1; src log = log) or line; d_alpha = n QM31. */
+int frieda_pass_fold(frieda_ctx *ctx, const uint32_t *d_src, uint32_t log, int is_circle, size_t n,
+                     const frieda_qm31 *d_alpha, uint32_t *d_dst);
+/* Twiddle tree of Coset::half_odds(k): copies 2^k forward and 2^k inverse twiddles to host. */
+int frieda_twiddles(frieda_ctx *ctx, uint32_t k, uint32_t *tw_out, uint32_t *itw_out);
+
+/* ---- introspection of the last frieda_prove* / frieda_fri_commit* wave (tests only) ----
+ * what: 0 coefficients (4*2^poly_log u32), 1 layer columns (layer, 4*2^log u32),
+ *       2 tree level (layer, level; 2^level*32 bytes), 3 alpha (layer; 16 bytes),
+ *       4 channel digest after the FRI commit phase (32 bytes), 5 nonce (8 bytes),
+ *       6 query positions (u32 each).  Returns bytes written or negative error. */
+long frieda_debug_fetch(frieda_ctx *ctx, int what, size_t blob, uint32_t layer, uint32_t level, void *out,
+                        size_t cap);
+/* Keep full per-layer state of the next wave resident for frieda_debug_fetch (default off). */
+int frieda_ctx_set_debug_keep(frieda_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/frieda_b200.h
+declares, refuses to compute without a GPU (no CPU fallback), and its host-only verifier and proof
+codec agree with the oracle on oracle-generated proofs.  No device compute here."""
+import os
+import re
+
+import pytest
+
+import frieda_b200 as F
+from frieda_b200 import api
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = (1 << 31) - 1
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "frieda_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(frieda_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    lib = F.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"libfrieda_b200.so does not export {name}"
+    assert sorted(api.EXPORTS) == declared
+
+
+def test_product_does_not_reference_the_oracle():
+    # the oracle is test infrastructure: nothing under frieda_b200/ may import, link or execute it
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "frieda_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "frieda_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(F.FriedaError) as ei:
+        F.Context(0)
+    assert ei.value.code == api.ERR_CUDA
+    with pytest.raises(F.FriedaError):
+        F.commit(b"abc", 4)
+
+
+def test_n_inner_layers_shape():
+    lib = F.load_library()
+    import ctypes as C
+    cfg = F.PcsConfig(4, 0, 20, 20)
+    assert lib.frieda_fri_n_inner_layers(131072, C.byref(cfg)) == 13
+    assert lib.frieda_fri_n_inner_layers(262146, C.byref(cfg)) == 14      # C1, log_last 0
+    cfg1 = F.PcsConfig(4, 1, 20, 20)
+    assert lib.frieda_fri_n_inner_layers(262146, C.byref(cfg1)) == 13     # C1, log_last 1
+    assert lib.frieda_fri_n_inner_layers(2, C.byref(cfg)) == api.ERR_PANIC  # reference panics
+
+
+@pytest.fixture(scope="module")
+def oracle_proof(blob_bytes):
+    cfg = O.make_config(4, 1, 20, 20)
+    _, pr = O.prove(blob_bytes, None, cfg)
+    return pr
+
+
+def test_proof_codec_roundtrip(oracle_proof):
+    b = oracle_proof.serialize()
+    p = F.Proof.deserialize(b)
+    assert p.serialize() == b
+    assert p.clone().serialize() == b
+    assert p.n_inner_layers == 13 and p.log_size_bound == 15
+    with pytest.raises(F.FriedaError):
+        F.Proof.deserialize(b[:-1])
+    with pytest.raises(F.FriedaError):
+        F.Proof.deserialize(b"XXXX" + b[4:])
+
+
+def test_host_verifier_matches_reference_test_suite(oracle_proof):
+    p = F.Proof.deserialize(oracle_proof.serialize())
+    assert F.verify_proof(p, None)                               # src/proof.rs:136-141
+    q = p.clone()
+    q.proof_of_work += 1
+    assert not F.verify_proof(q, None)                           # :143-149
+    ev = p.evaluations
+    q = p.clone()
+    q.set_evaluation(0, [(x + 1) % P for x in ev[0]])
+    assert not F.verify_proof(q, None)                           # :151-157
+    q = p.clone()
+    for i, e in enumerate(reversed(ev)):
+        q.set_evaluation(i, e)
+    assert not F.verify_proof(q, None)                           # :158-164
+    q = p.clone()
+    q.set_evaluation(0, ev[1])
+    q.set_evaluation(1, ev[0])
+    assert not F.verify_proof(q, None)                           # :175-181
+    q = p.clone()
+    q.pop_evaluation()
+    with pytest.raises(F.ReferencePanic):                        # :166-173
+        F.verify_proof(q, None)
+    q.c.n_evaluations += 1
+    assert not F.verify_proof(p, 7)                              # wrong seed
+
+
+def test_host_verifier_seed_binding(blob_bytes):
+    cfg = O.make_config(4, 1, 20, 20)
+    _, p1 = O.prove(blob_bytes, 1, cfg)
+    _, p2 = O.prove(blob_bytes, 2, cfg)
+    f1, f2 = F.Proof.deserialize(p1.serialize()), F.Proof.deserialize(p2.serialize())
+    assert F.verify_proof(f1, 1) and F.verify_proof(f2, 2)       # src/proof.rs:183-193
+    assert not F.verify_proof(f1, 2) and not F.verify_proof(f2, 1)
+
+
+def test_host_verifier_rejects_witness_tampering(oracle_proof):
+    p = F.Proof.deserialize(oracle_proof.serialize())
+    q = p.clone()
+    q.c.first_layer.hash_witness[5] ^= 1
+    assert not F.verify_proof(q, None)
+    q = p.clone()
+    q.c.inner_layers[3].fri_witness[0].v[2] ^= 1
+    assert not F.verify_proof(q, None)
+    q = p.clone()
+    q.c.inner_layers[0].commitment[0] ^= 1
+    assert not F.verify_proof(q, None)
+    q = p.clone()
+    q.c.last_layer_poly[0].v[0] ^= 1
+    assert not F.verify_proof(q, None)
+    q = p.clone()
+    q.c.n_inner_layers -= 1
+    assert not F.verify_proof(q, None)
+    q.c.n_inner_layers += 1
+
+
+@pytest.mark.parametrize("case", ["pattern_1024_seedlen", "e2e_string", "pattern_3000_b2_l2"])
+def test_host_verifier_on_other_shapes(case, golden):
+    g = next(x for x in golden["oracle_generated"]["prove"] if x["name"] == case)
+    if case == "e2e_string":
+        data = b"This is the original data that needs to be made available."
+    else:
+        data = bytes(i % 256 for i in range(g["len"]))
+    cfg = O.make_config(*g["cfg"])
+    _, pr = O.prove(data, g["seed"], cfg)
+    p = F.Proof.deserialize(pr.serialize())
+    assert F.verify_proof(p, g["seed"])
+    assert not F.verify_proof(p, (g["seed"] or 0) + 1)

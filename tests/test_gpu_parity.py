@@ -1,0 +1,502 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs,
+bit-exact, on every intermediate (coefficients, twiddles, evaluations, every Merkle level, every
+FRI layer, alphas, nonce, queries, witnesses), plus the reference's own test behaviours
+(src/commit.rs:28-38, src/proof.rs:119-193, src/lib.rs:52-85) through the product API."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import frieda_b200 as F
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+P = (1 << 31) - 1
+
+
+def pattern(n):
+    return bytes(i % 256 for i in range(n))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = F.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def first_diff(a, b):
+    a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
+    if a.shape != b.shape:
+        return f"shape {a.shape} vs {b.shape}"
+    d = np.nonzero(a != b)[0]
+    return None if d.size == 0 else f"{d.size} mismatches, first at {int(d[0])}: {a[d[0]]} vs {b[d[0]]}"
+
+
+# ------------------------------------------------------------------ twiddles
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 7, 12, 17])
+def test_twiddles(ctx, k):
+    tw, itw = ctx.twiddles(k)
+    otw, oitw = O.precompute_twiddles(k)
+    assert first_diff(tw, otw) is None
+    assert first_diff(itw, oitw) is None
+
+
+def test_twiddles_small_after_large(ctx):
+    ctx.twiddles(18)
+    tw, itw = ctx.twiddles(9)  # served from the tail of the cached larger tree
+    otw, oitw = O.precompute_twiddles(9)
+    assert first_diff(tw, otw) is None and first_diff(itw, oitw) is None
+
+
+# ------------------------------------------------------------------ commit (KAT + vectors)
+def test_commit_blob_golden_root(ctx, blob_bytes, golden):
+    # the reference's only known-answer test: src/commit.rs:28-38
+    assert ctx.commit(blob_bytes, 4).hex() == golden["reference_certified"]["commit_blob_blowup4"]
+
+
+def test_commit_survey_vectors(ctx, golden):
+    sp = golden["survey_probe"]
+    assert ctx.commit(pattern(1024), 4).hex() == sp["commit_pattern_1024"]
+    assert ctx.commit(pattern(65536), 4).hex() == sp["commit_pattern_65536"]
+    assert ctx.commit(pattern(131072), 4).hex() == sp["commit_pattern_131072"]
+    assert ctx.commit(bytes(131072), 4).hex() == sp["commit_zeros_131072"]
+    assert ctx.commit(b"This is the original data that needs to be made available.", 4).hex() == sp[
+        "commit_e2e_string"]
+
+
+def test_commit_golden_vector_file(ctx, golden):
+    for c in golden["oracle_generated"]["commit"]:
+        name = c["name"]
+        if name == "empty":
+            data = b""
+        elif name == "one_byte":
+            data = b"\x07"
+        elif name.startswith("splitmix"):
+            state = {"splitmix_c2": 0x4652494544410000, "splitmix_c2_b1": 0x4652494544410001,
+                     "splitmix_1MiB_b2": 0x4652494544414236}[name]
+            data = O.splitmix64_bytes(state, c["len"])
+        else:
+            data = pattern(c["len"])
+        assert ctx.commit(data, c["log_blowup"]).hex() == c["root"], name
+
+
+@pytest.mark.parametrize("n,blow", [(0, 1), (1, 1), (1, 2), (3, 1), (4, 3), (15, 1), (16, 1), (17, 4), (29, 2), (30, 2),
+                                    (31, 5), (100, 1), (257, 4), (1000, 2), (4097, 3), (16385, 4), (70000, 1)])
+def test_commit_ragged_sizes_vs_oracle(ctx, n, blow):
+    rng = np.random.default_rng(n * 7 + blow)
+    data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    assert ctx.commit(data, blow) == O.commit(data, blow)
+
+
+def test_commit_panics_like_reference(ctx):
+    with pytest.raises(F.ReferencePanic):
+        ctx.commit(b"\x01", 0)  # Coset::half_odds(0 + 0 - 1)
+
+
+def test_commit_batch_vs_oracle(ctx):
+    rng = np.random.default_rng(5)
+    for blob_len, n, blow in [(1000, 7, 3), (4096, 33, 4), (131072, 5, 4)]:
+        blobs = rng.integers(0, 256, (n, blob_len), dtype=np.uint8)
+        roots = ctx.commit_batch(blobs, blow)
+        for i in range(n):
+            assert roots[i].tobytes() == O.commit(blobs[i].tobytes(), blow), (blob_len, i)
+
+
+def test_commit_batch_strided_and_waves(ctx):
+    rng = np.random.default_rng(6)
+    n, blob_len = 20, 5000
+    big = rng.integers(0, 256, (n, blob_len + 24), dtype=np.uint8)
+    view = big[:, :blob_len]  # stride > len
+    ctx.set_workspace_limit(3 * (1 << 20))  # forces several waves
+    try:
+        roots = ctx.commit_batch(view, 4)
+    finally:
+        ctx.set_workspace_limit(0)
+    for i in range(n):
+        assert roots[i].tobytes() == O.commit(view[i].tobytes(), 4), i
+
+
+def test_commit_batch_device_pointers(ctx, torch_mod):
+    torch = torch_mod
+    rng = np.random.default_rng(8)
+    n, blob_len = 16, 131072
+    blobs = rng.integers(0, 256, (n, blob_len), dtype=np.uint8)
+    d_in = torch.from_numpy(blobs).cuda()
+    d_out = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.commit_batch_ptr(d_in.data_ptr(), blob_len, blob_len, n, 4, d_out.data_ptr(), device=True)
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    got = d_out.cpu().numpy()
+    want = ctx.commit_batch(blobs, 4)
+    assert first_diff(got, want) is None
+    assert got[3].tobytes() == O.commit(blobs[3].tobytes(), 4)
+
+
+# ------------------------------------------------------------------ standalone passes
+@pytest.mark.parametrize("p,beta,nz_frac", [(0, 3, 1.0), (1, 2, 1.0), (2, 1, 1.0), (1, 1, 1.0), (0, 1, 1.0), (3, 2, 1.0),
+                                            (5, 4, 0.6), (10, 1, 1.0), (11, 3, 0.3), (14, 4, 0.53), (15, 2, 1.0),
+                                            (16, 1, 0.55), (17, 2, 0.9)])
+def test_lde_pass_vs_oracle_fft(ctx, torch_mod, p, beta, nz_frac):
+    torch = torch_mod
+    rng = np.random.default_rng(p * 31 + beta)
+    n_blobs = 2
+    n4 = 1 << p
+    n_felts = max(1, int(4 * n4 * nz_frac))
+    coef = np.zeros((n_blobs, 4 * n4), dtype=np.uint32)
+    coef[:, :n_felts] = rng.integers(0, P, (n_blobs, n_felts), dtype=np.uint32)
+    D = p + beta
+    d_coef = torch.from_numpy(coef.view(np.int32)).cuda()
+    d_eval = torch.zeros((n_blobs, 4 << D), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.pass_lde(d_coef.data_ptr(), p, beta, n_blobs, n_felts, d_eval.data_ptr())
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    got = d_eval.cpu().numpy().view(np.uint32).reshape(n_blobs, 4, 1 << D)
+    for b in range(n_blobs):
+        for c in range(4):
+            want = O.circle_fft(coef[b, c * n4:(c + 1) * n4], D)
+            assert first_diff(got[b, c], want) is None, (b, c, first_diff(got[b, c], want))
+
+
+def test_lde_linearity_full_size(ctx, torch_mod):
+    # size-independent property at C2's full size: LDE(a + b) == LDE(a) + LDE(b) (mod P)
+    torch = torch_mod
+    rng = np.random.default_rng(77)
+    p, beta = 14, 4
+    a = rng.integers(0, P, 4 << p, dtype=np.uint32)
+    b = rng.integers(0, P, 4 << p, dtype=np.uint32)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    coef = np.stack([a, b, s])
+    d_coef = torch.from_numpy(coef.view(np.int32)).cuda()
+    d_eval = torch.zeros((3, 4 << (p + beta)), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.pass_lde(d_coef.data_ptr(), p, beta, 3, 4 << p, d_eval.data_ptr())
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    ev = d_eval.cpu().numpy().view(np.uint32).astype(np.uint64)
+    assert np.array_equal((ev[0] + ev[1]) % P, ev[2])
+    assert ev.max() < P
+
+
+@pytest.mark.parametrize("log", [0, 1, 2, 5, 9, 10, 11, 13, 21])
+def test_merkle_pass_vs_oracle(ctx, torch_mod, log):
+    torch = torch_mod
+    rng = np.random.default_rng(log)
+    n_blobs = 2 if log < 20 else 1
+    cols = rng.integers(0, P, (n_blobs, 4, 1 << log), dtype=np.uint32)
+    d_cols = torch.from_numpy(cols.view(np.int32)).cuda()
+    d_roots = torch.zeros((n_blobs, 32), dtype=torch.uint8, device="cuda")
+    keep = log <= 13
+    d_tree = torch.zeros((n_blobs, 2 << log, 32), dtype=torch.uint8, device="cuda") if keep else None
+    torch.cuda.synchronize()
+    ctx.pass_merkle(d_cols.data_ptr(), log, n_blobs, d_tree.data_ptr() if keep else None, d_roots.data_ptr())
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    roots = d_roots.cpu().numpy()
+    # oracle tree through hashlib-free restatement: reuse oracle's compress
+    for b in range(n_blobs):
+        level = [None] * (log + 1)
+        leaves = np.zeros((1 << log, 8), dtype=np.uint32)
+        if log <= 13:
+            for i in range(1 << log):
+                m = [int(cols[b, c, i]) for c in range(4)] + [0] * 12
+                leaves[i] = O.blake2s_compress([0] * 8, m)
+            level[log] = leaves
+            for k in range(log - 1, -1, -1):
+                cur = np.zeros((1 << k, 8), dtype=np.uint32)
+                for i in range(1 << k):
+                    m = [int(x) for x in level[k + 1][2 * i]] + [int(x) for x in level[k + 1][2 * i + 1]]
+                    cur[i] = O.blake2s_compress([0] * 8, m)
+                level[k] = cur
+            assert roots[b].tobytes() == level[0].astype("<u4").tobytes()
+            tree = d_tree[b].cpu().numpy()
+            for k in range(log + 1):
+                got = tree[(1 << k):(2 << k)].reshape(-1)
+                want = np.frombuffer(level[k].astype("<u4").tobytes(), dtype=np.uint8)
+                assert first_diff(got, want) is None, (k, first_diff(got, want))
+    if log == 21:
+        # large tree: root only, against the oracle's own tree over the same columns via a commit-shaped check
+        # (idempotence: two runs agree, and the kept-tree variant agrees with the truncated one)
+        d_tree2 = torch.zeros((1, 2 << log, 32), dtype=torch.uint8, device="cuda")
+        d_roots2 = torch.zeros((1, 32), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.pass_merkle(d_cols.data_ptr(), log, 1, d_tree2.data_ptr(), d_roots2.data_ptr())
+        torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+        assert d_roots2.cpu().numpy().tobytes() == roots.tobytes()
+        t = d_tree2[0].cpu().numpy()
+        assert t[1].tobytes() == roots[0].tobytes()
+        # spot-check one path from a leaf to the root with the oracle's compression
+        i = 123457
+        m = [int(cols[0, c, i]) for c in range(4)] + [0] * 12
+        h = np.array(O.blake2s_compress([0] * 8, m), dtype="<u4").tobytes()
+        assert t[(1 << log) + i].tobytes() == h
+        for k in range(log - 1, -1, -1):
+            j = i >> (log - k)
+            l, r = t[(2 << k) + 2 * j], t[(2 << k) + 2 * j + 1]
+            m = list(np.frombuffer(l.tobytes() + r.tobytes(), dtype="<u4"))
+            h = np.array(O.blake2s_compress([0] * 8, [int(x) for x in m]), dtype="<u4").tobytes()
+            assert t[(1 << k) + j].tobytes() == h, k
+
+
+# ------------------------------------------------------------------ FRI commit phase, every intermediate
+CASES = [
+    ("pattern", 1024, 1024, (4, 0, 20, 20)),
+    ("pattern", 3000, 5, (2, 2, 33, 8)),
+    ("pattern", 65536, 65536, (4, 0, 20, 20)),
+    ("e2e", 58, None, (4, 0, 20, 20)),
+    ("pattern", 200, 3, (1, 0, 5, 3)),
+    ("pattern", 40000, None, (3, 1, 17, 10)),
+]
+
+
+def case_data(kind, n):
+    if kind == "e2e":
+        return b"This is the original data that needs to be made available."
+    return pattern(n)
+
+
+@pytest.mark.parametrize("kind,n,seed,cfg", CASES)
+def test_fri_commit_every_intermediate(ctx, kind, n, seed, cfg):
+    data = case_data(kind, n)
+    ocfg = O.make_config(*cfg)
+    t = O.trace(data, seed, ocfg, stop_after_fri=True, with_trees=True)
+    blobs = np.frombuffer(data, dtype=np.uint8).reshape(1, -1).copy()
+    ctx.set_debug_keep(True)
+    try:
+        roots, last = ctx.fri_commit_batch(blobs, None if seed is None else [seed], F.PcsConfig(*cfg))
+        n_layers = len(t.layer_logs)
+        assert roots.shape[1] == n_layers
+        coef = ctx.debug_fetch(0, 0, 0, 0, 16 << t.poly_log).view(np.uint32)
+        assert first_diff(coef, t.coeffs) is None, "coefficients: " + str(first_diff(coef, t.coeffs))
+        for layer in range(n_layers):
+            lg = t.layer_logs[layer]
+            cols = ctx.debug_fetch(1, 0, layer, 0, 16 << lg).view(np.uint32).reshape(4, -1)
+            d = first_diff(cols, t.layer_columns[layer])
+            assert d is None, f"layer {layer} columns: {d}"
+            for level in range(lg, -1, -1):
+                got = ctx.debug_fetch(2, 0, layer, level, 32 << level)
+                d = first_diff(got, t.tree_levels[layer][level])
+                assert d is None, f"layer {layer} tree level {level}: {d}"
+            assert roots[0, layer].tobytes() == t.tree_levels[layer][0].tobytes(), f"root of layer {layer}"
+            alpha = tuple(int(x) for x in ctx.debug_fetch(3, 0, layer, 0, 16).view(np.uint32))
+            assert alpha == t.alphas[layer], f"alpha of layer {layer}"
+        last_cols = ctx.debug_fetch(1, 0, n_layers, 0, 16 << (cfg[0] + cfg[1])).view(np.uint32).reshape(4, -1)
+        assert first_diff(last_cols, t.last_eval) is None, "last evaluation"
+        assert [tuple(int(x) for x in q) for q in last[0]] == t.last_layer_poly
+        assert ctx.debug_fetch(4, 0, 0, 0, 32).tobytes() == t.digest_after_fri
+    finally:
+        ctx.set_debug_keep(False)
+
+
+def test_fri_commit_blob_layers(ctx, blob_bytes, golden):
+    g = next(x for x in golden["oracle_generated"]["prove"] if x["name"] == "blob_4_1_20_20")
+    blobs = np.frombuffer(blob_bytes, dtype=np.uint8).reshape(1, -1).copy()
+    roots, last = ctx.fri_commit_batch(blobs, None, F.PcsConfig(4, 1, 20, 20))
+    assert [r.tobytes().hex() for r in roots[0]] == g["layer_roots"]
+    assert [[int(x) for x in q] for q in last[0]] == g["last_layer_poly"]
+    assert roots[0, 0].tobytes().hex() == golden["reference_certified"]["commit_blob_blowup4"]
+
+
+def test_fri_commit_batch_with_seeds_vs_oracle(ctx):
+    cfg = (4, 0, 20, 20)
+    n, blob_len = 6, 131072
+    blobs = np.stack([np.frombuffer(O.splitmix64_bytes(0x4652494544410000 + b, blob_len), dtype=np.uint8)
+                      for b in range(n)])
+    seeds = list(range(n))
+    roots, last = ctx.fri_commit_batch(blobs, seeds, F.PcsConfig(*cfg))
+    for b in range(n):
+        oroots, olast = O.fri_commit(blobs[b].tobytes(), seeds[b], O.make_config(*cfg))
+        assert [r.tobytes() for r in roots[b]] == oroots, b
+        assert [tuple(int(x) for x in q) for q in last[b]] == olast, b
+
+
+def test_fri_commit_device_pointers(ctx, torch_mod):
+    torch = torch_mod
+    cfg = F.PcsConfig(4, 0, 20, 20)
+    n, blob_len = 4, 131072
+    blobs = np.stack([np.frombuffer(O.splitmix64_bytes(0x4652494544410000 + b, blob_len), dtype=np.uint8)
+                      for b in range(n)])
+    L = 1 + ctx.n_inner_layers(blob_len, cfg)
+    d_in = torch.from_numpy(blobs).cuda()
+    d_roots = torch.zeros((n, L, 32), dtype=torch.uint8, device="cuda")
+    d_last = torch.zeros((n, 1, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.fri_commit_batch_ptr(d_in.data_ptr(), blob_len, blob_len, n, None, cfg, d_roots.data_ptr(),
+                             d_last.data_ptr(), device=True)
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    roots, last = ctx.fri_commit_batch(blobs, None, cfg)
+    assert first_diff(d_roots.cpu().numpy(), roots) is None
+    assert first_diff(d_last.cpu().numpy().view(np.uint32), last) is None
+
+
+def test_fri_reference_panic_shapes(ctx):
+    with pytest.raises(F.ReferencePanic):
+        ctx.fri_commit_batch(np.zeros((1, 2), dtype=np.uint8), None, F.PcsConfig(4, 0, 20, 4))
+
+
+# ------------------------------------------------------------------ proofs
+def check_proof_vs_oracle(ctx, data, seed, cfg):
+    ocfg = O.make_config(*cfg)
+    t = O.trace(data, seed, ocfg, with_trees=False)
+    root, pr = ctx.commit_and_generate_proof(data, seed, F.PcsConfig(*cfg))
+    assert root == t.root
+    assert pr.proof_of_work == t.nonce, f"nonce {pr.proof_of_work} vs {t.nonce}"
+    nq = len(t.queries)
+    got_q = ctx.debug_fetch(6, 0, 0, 0, 4 * cfg[2]).view(np.uint32)
+    assert first_diff(got_q, t.queries) is None, "queries"
+    assert len(pr.evaluations) == nq
+    assert pr.last_layer_poly == t.last_layer_poly
+    assert pr.serialize() == t.proof_bytes, "serialized proof differs from the oracle's"
+    return pr
+
+
+@pytest.mark.parametrize("kind,n,seed,cfg", CASES)
+def test_proof_bit_exact_vs_oracle(ctx, kind, n, seed, cfg):
+    data = case_data(kind, n)
+    pr = check_proof_vs_oracle(ctx, data, seed, cfg)
+    assert F.verify_proof(pr, seed)
+    assert not F.verify_proof(pr, (seed or 0) + 1)
+
+
+def test_proof_golden_vector_file(ctx, blob_bytes, golden):
+    for g in golden["oracle_generated"]["prove"]:
+        name = g["name"]
+        if name.startswith("blob"):
+            data = blob_bytes
+        elif name == "e2e_string":
+            data = b"This is the original data that needs to be made available."
+        elif name.startswith("splitmix_c4_b"):
+            data = O.splitmix64_bytes(0x4652494544410000 + int(name.rsplit("b", 1)[1]), g["len"])
+        else:
+            data = pattern(g["len"])
+        root, pr = ctx.commit_and_generate_proof(data, g["seed"], F.PcsConfig(*g["cfg"]))
+        assert root.hex() == g["root"], name
+        assert pr.proof_of_work == g["nonce"], name
+        assert [list(q) for q in pr.last_layer_poly] == g["last_layer_poly"], name
+        assert [pr.first_layer_commitment.hex()] + [c.hex() for c in pr.inner_layer_commitments] == g[
+            "layer_roots"], name
+        b = pr.serialize()
+        assert len(b) == g["proof_len"] and hashlib.sha256(b).hexdigest() == g["proof_sha256"], name
+        assert F.verify_proof(pr, g["seed"]), name
+
+
+PCS = (4, 1, 20, 20)  # src/proof.rs:109-116
+
+
+@pytest.fixture(scope="module")
+def blob_proof(ctx, blob_bytes):
+    return ctx.commit_and_generate_proof(blob_bytes, None, F.PcsConfig(*PCS))
+
+
+def test_generate_proof(blob_proof):
+    assert blob_proof[1].n_inner_layers != 0                      # src/proof.rs:119-124
+
+
+def test_commit_and_generate_proof(ctx, blob_bytes, blob_proof):
+    root, pr = blob_proof                                         # src/proof.rs:126-135
+    assert root == ctx.commit(blob_bytes, PCS[0])
+    assert pr.first_layer_commitment == root
+
+
+def test_verify_proof(blob_proof):
+    assert F.verify_proof(blob_proof[1], None)                    # src/proof.rs:136-141
+
+
+def test_verify_proof_with_invalid_pow(blob_proof):
+    p = blob_proof[1].clone()
+    p.proof_of_work += 1
+    assert not F.verify_proof(p, None)                            # :143-149
+
+
+def test_verify_proof_with_invalid_evaluations(blob_proof):
+    p = blob_proof[1].clone()
+    p.set_evaluation(0, [(x + 1) % P for x in p.evaluations[0]])
+    assert not F.verify_proof(p, None)                            # :151-157
+
+
+def test_verify_proof_with_invalid_evaluations_order(blob_proof):
+    p = blob_proof[1].clone()
+    ev = p.evaluations
+    for i, e in enumerate(reversed(ev)):
+        p.set_evaluation(i, e)
+    assert not F.verify_proof(p, None)                            # :158-164
+
+
+def test_verify_proof_with_invalid_evaluations_length(blob_proof):
+    p = blob_proof[1].clone()
+    p.pop_evaluation()
+    with pytest.raises(F.ReferencePanic):                         # :166-173 (#[should_panic])
+        F.verify_proof(p, None)
+    p.c.n_evaluations += 1
+
+
+def test_verify_proof_with_invalid_1_evaluation_unordered(blob_proof):
+    p = blob_proof[1].clone()
+    ev = p.evaluations
+    p.set_evaluation(0, ev[1])
+    p.set_evaluation(1, ev[0])
+    assert not F.verify_proof(p, None)                            # :175-181
+
+
+def test_verify_proof_with_seed(ctx, blob_bytes):
+    cfg = F.PcsConfig(*PCS)                                       # src/proof.rs:183-193
+    p1 = ctx.generate_proof(blob_bytes, 1, cfg)
+    p2 = ctx.generate_proof(blob_bytes, 2, cfg)
+    assert p1.evaluations != p2.evaluations
+    assert F.verify_proof(p1, 1) and F.verify_proof(p2, 2)
+    assert not F.verify_proof(p1, 2) and not F.verify_proof(p2, 1)
+
+
+def test_end_to_end(ctx):
+    data = b"This is the original data that needs to be made available."   # src/lib.rs:52-85
+    cfg = F.PcsConfig(4, 0, 20, 20)
+    commitment = ctx.commit(data, 4)
+    proof = ctx.generate_proof(data, None, cfg)
+    assert proof.first_layer_commitment == commitment
+    assert F.verify_proof(proof, None)
+
+
+def test_oracle_verifier_accepts_gpu_proof(ctx, blob_bytes):
+    cfg = (4, 1, 20, 20)
+    _, pr = ctx.commit_and_generate_proof(blob_bytes, 3, F.PcsConfig(*cfg))
+    _, opr = O.prove(blob_bytes, 3, O.make_config(*cfg))
+    assert pr.serialize() == opr.serialize()
+    assert O.verify(opr, 3)
+
+
+def test_prove_batch_c4_vs_oracle(ctx):
+    # BASELINE config 4: 64 queries per blob, seed = blob index, batched
+    cfg = (4, 0, 64, 20)
+    n, blob_len = 8, 131072
+    blobs = np.stack([np.frombuffer(O.splitmix64_bytes(0x4652494544410000 + b, blob_len), dtype=np.uint8)
+                      for b in range(n)])
+    seeds = list(range(n))
+    roots, proofs = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    for b in (0, 3, 7):
+        oroot, opr = O.prove(blobs[b].tobytes(), seeds[b], O.make_config(*cfg))
+        assert roots[b].tobytes() == oroot
+        assert proofs[b].serialize() == opr.serialize(), b
+    for b in range(n):
+        assert F.verify_proof(proofs[b], seeds[b])
+        assert not F.verify_proof(proofs[b], seeds[b] + 1)
+
+
+def test_prove_batch_in_waves(ctx):
+    cfg = (3, 0, 9, 6)
+    rng = np.random.default_rng(11)
+    n, blob_len = 9, 3000
+    blobs = rng.integers(0, 256, (n, blob_len), dtype=np.uint8)
+    seeds = [100 + i for i in range(n)]
+    ctx.set_workspace_limit(3 * (1 << 20))
+    try:
+        roots, proofs = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    finally:
+        ctx.set_workspace_limit(0)
+    for b in range(n):
+        oroot, opr = O.prove(blobs[b].tobytes(), seeds[b], O.make_config(*cfg))
+        assert roots[b].tobytes() == oroot and proofs[b].serialize() == opr.serialize(), b
