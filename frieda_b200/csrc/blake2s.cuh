@@ -36,34 +36,51 @@ inline uint32_t rotr7(uint32_t x) { return rotr_(x, 7); }
 #define FR_B2S_IV6 0x1F83D9ABu
 #define FR_B2S_IV7 0x5BE0CD19u
 
-#define FR_G(a, b, c, d, x, y) \
-  do {                         \
-    a = a + b + (x);           \
-    d = rotr16(d ^ a);         \
-    c = c + d;                 \
-    b = rotr12(b ^ c);         \
-    a = a + b + (y);           \
-    d = rotr8(d ^ a);          \
-    c = c + d;                 \
-    b = rotr7(b ^ c);          \
+// Pipe balance (measured on B200, bench_micro/pipes.cu): LOP3 / SHF / PRMT / IADD3 issue at 0.5
+// warp-instructions per clock per SM sub-partition on the ALU pipe, IMAD at 0.5 on the FMA pipe, and
+// the two overlap (a 1:1 mix reaches 0.98).  A G function needs 4 xors + 4 rotates that only the ALU
+// pipe can do, so the 6 adds go to the FMA pipe as IMAD x * one + y with `one` an opaque runtime 1
+// (otherwise ptxas folds half of them back into ALU-pipe IADD3s).  MASK marks the message words that
+// may be non-zero; adds of the others are dropped at compile time.
+#if defined(__CUDA_ARCH__)
+FR_D uint32_t fr_add(uint32_t x, uint32_t y, uint32_t one) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+  return r;
+}
+#else
+inline uint32_t fr_add(uint32_t x, uint32_t y, uint32_t) { return x + y; }
+#endif
+
+#define FR_MADD(a, s) ((((MASK) >> (s)) & 1u) ? fr_add(a, m[s], one) : (a))
+#define FR_G(a, b, c, d, sx, sy)   \
+  do {                             \
+    a = fr_add(FR_MADD(a, sx), b, one); \
+    d = rotr16(d ^ a);             \
+    c = fr_add(c, d, one);         \
+    b = rotr12(b ^ c);             \
+    a = fr_add(FR_MADD(a, sy), b, one); \
+    d = rotr8(d ^ a);              \
+    c = fr_add(c, d, one);         \
+    b = rotr7(b ^ c);              \
   } while (0)
 
 #define FR_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
   do {                                                                                  \
-    FR_G(v0, v4, v8, v12, m[s0], m[s1]);                                                \
-    FR_G(v1, v5, v9, v13, m[s2], m[s3]);                                                \
-    FR_G(v2, v6, v10, v14, m[s4], m[s5]);                                               \
-    FR_G(v3, v7, v11, v15, m[s6], m[s7]);                                               \
-    FR_G(v0, v5, v10, v15, m[s8], m[s9]);                                               \
-    FR_G(v1, v6, v11, v12, m[s10], m[s11]);                                             \
-    FR_G(v2, v7, v8, v13, m[s12], m[s13]);                                              \
-    FR_G(v3, v4, v9, v14, m[s14], m[s15]);                                              \
+    FR_G(v0, v4, v8, v12, s0, s1);                                                      \
+    FR_G(v1, v5, v9, v13, s2, s3);                                                      \
+    FR_G(v2, v6, v10, v14, s4, s5);                                                     \
+    FR_G(v3, v7, v11, v15, s6, s7);                                                     \
+    FR_G(v0, v5, v10, v15, s8, s9);                                                     \
+    FR_G(v1, v6, v11, v12, s10, s11);                                                   \
+    FR_G(v2, v7, v8, v13, s12, s13);                                                    \
+    FR_G(v3, v4, v9, v14, s14, s15);                                                    \
   } while (0)
 
-// h <- compress(h, m, t0, t1, f0, f1).  Fully unrolled; with constant zeros in h / m the
-// compiler folds the corresponding adds away (leaf messages carry 4 words, grind messages 2).
-FR_HD void blake2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
-                            uint32_t f1) {
+// h <- compress(h, m, t0, t1, f0, f1).  Fully unrolled, state in registers.
+template <uint32_t MASK>
+FR_HD void blake2s_compress_t(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
+                              uint32_t f1, uint32_t one) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   uint32_t v8 = FR_B2S_IV0, v9 = FR_B2S_IV1, v10 = FR_B2S_IV2, v11 = FR_B2S_IV3;
   uint32_t v12 = FR_B2S_IV4 ^ t0, v13 = FR_B2S_IV5 ^ t1, v14 = FR_B2S_IV6 ^ f0, v15 = FR_B2S_IV7 ^ f1;
@@ -86,19 +103,24 @@ FR_HD void blake2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, ui
   h[6] ^= v6 ^ v14;
   h[7] ^= v7 ^ v15;
 }
+FR_HD void blake2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
+                            uint32_t f1, uint32_t one = 1u) {
+  blake2s_compress_t<0xFFFFu>(h, m, t0, t1, f0, f1, one);
+}
 
 // Merkle leaf over the 4 coordinate columns: hash_node(None, [c0, c1, c2, c3]).
-FR_HD void merkle_hash_leaf(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[8]) {
+FR_HD void merkle_hash_leaf(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[8],
+                            uint32_t one = 1u) {
   uint32_t m[16] = {c0, c1, c2, c3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 8; i++) out[i] = 0;
-  blake2s_compress(out, m, 0, 0, 0, 0);
+  blake2s_compress_t<0x000Fu>(out, m, 0, 0, 0, 0, one);
 }
 // Merkle inner node: hash_node(Some((left, right)), []); m = left || right.
-FR_HD void merkle_hash_node(const uint32_t m[16], uint32_t out[8]) {
+FR_HD void merkle_hash_node(const uint32_t m[16], uint32_t out[8], uint32_t one = 1u) {
 #pragma unroll
   for (int i = 0; i < 8; i++) out[i] = 0;
-  blake2s_compress(out, m, 0, 0, 0, 0);
+  blake2s_compress_t<0xFFFFu>(out, m, 0, 0, 0, 0, one);
 }
 
 // ---- Blake2sChannel ------------------------------------------------------

@@ -48,6 +48,7 @@ struct Bump {
 struct Plan {
   Geom g;
   size_t B = 0;
+  uint32_t levels_cfg = 10;  // Merkle per-pass depth chosen for this call
   uint32_t nq = 0;  // n_queries (prove)
   bool keep = false, prove = false, fri = false;
   size_t in_stride = 0;  // bytes between staged blobs
@@ -61,12 +62,18 @@ struct Plan {
 
 uint32_t layer_log(const Geom &g, uint32_t layer) { return g.D - layer; }
 
-size_t tree_slots(uint32_t d, bool keep) {
+// Levels reduced inside one CTA of the Merkle bottom/middle passes.  Deep (10: 1024 leaves -> 1
+// node) minimises launches but parks most warps at barriers during the last 8 levels; shallow
+// (2: 1024 -> 256) keeps every thread hashing in every level at the cost of more passes.
+uint32_t pass_levels(uint32_t d, uint32_t levels_cfg) {
+  uint32_t chunk = d < 10 ? d : 10;
+  return levels_cfg < chunk ? levels_cfg : chunk;
+}
+size_t tree_slots(uint32_t d, bool keep, uint32_t levels_cfg) {
   // kept trees hold every level; truncated trees only the levels above the bottom pass
   // (tail layers: just the root in slot 1)
   if (keep) return (size_t)2 << d;
-  uint32_t chunk = d < 10 ? d : 10;
-  return (size_t)2 << (d - chunk);
+  return (size_t)2 << (d - pass_levels(d, levels_cfg));
 }
 
 }  // namespace
@@ -77,6 +84,13 @@ struct frieda_ctx {
   std::string err;
   uint64_t launches = 0;
   size_t ws_limit = 0;
+  uint32_t merkle_levels_big = 3;    // per-pass depth for large batches (env FRIEDA_MERKLE_LEVELS)
+  uint32_t merkle_levels_small = 10; // per-pass depth when the grid would not fill the GPU anyway
+  uint32_t levels_for(size_t n_blobs, uint32_t d) const {
+    // CTAs of the bottom pass; below ~4 waves of 148 SMs x 4 CTAs the launch count matters more
+    size_t ctas = n_blobs << (d > 10 ? d - 10 : 0);
+    return ctas >= 2368 ? merkle_levels_big : merkle_levels_small;
+  }
   // twiddle cache
   bool tw_valid = false;
   uint32_t tw_K = 0;
@@ -248,7 +262,7 @@ void layout(Plan &pl, size_t B, bool stage_input) {
   }
   const uint32_t n_trees = pl.fri ? g.n_layers : 1;
   for (uint32_t l = 0; l < n_trees; l++) {
-    pl.tree_stride[l] = tree_slots(layer_log(g, l), pl.keep);
+    pl.tree_stride[l] = tree_slots(layer_log(g, l), pl.keep, pl.levels_cfg);
     pl.o_tree[l] = bp.take(B * pl.tree_stride[l] * 32);
   }
   pl.o_roots = bp.take(B * (size_t)(pl.fri ? g.n_layers : 1) * 32);
@@ -299,7 +313,40 @@ T *at(frieda_ctx *ctx, size_t off) {
   return reinterpret_cast<T *>(ctx->arena + off);
 }
 
-// Merkle tree over an existing or fused-folded layer: bottom chunks, middle passes, top.
+// Bottom pass (leaves from columns / fused fold), middle passes over existing nodes, then one CTA
+// per blob for the top of the tree (+ the channel step).  `mp` carries the source/destination/tree
+// pointers; sizes and depths are filled in here.
+int run_tree(frieda_ctx *ctx, int src, MerkleBottomParams mp, uint32_t d, uint32_t levels_cfg, bool keep,
+             size_t n_blobs, uint8_t *roots, size_t roots_stride, Channel *chan, QM31 *alpha, size_t alpha_stride) {
+  mp.log = d;
+  mp.chunk_log = d < 10 ? d : 10;
+  mp.levels = pass_levels(d, levels_cfg);
+  mp.src_level = d;
+  mp.write_all = keep ? 1 : 0;
+  KL(src == SRC_COLS ? "merkle_bottom_cols" : src == SRC_FOLD_CIRCLE ? "fold_circle+merkle_bottom" : "fold_line+merkle_bottom",
+     launch_merkle_bottom(ctx->stream, src, mp, n_blobs), 1);
+  uint32_t u = d - mp.levels;
+  while (u > 10) {
+    MerkleBottomParams mm = mp;
+    mm.src_cols = nullptr;
+    mm.dst_cols = nullptr;
+    mm.alpha = nullptr;
+    mm.log = u;
+    mm.src_level = u;
+    mm.chunk_log = 10;
+    mm.levels = levels_cfg < 10 ? levels_cfg : 10;
+    if (mm.levels > u - 10) mm.levels = u - 10;  // stop exactly where the top kernel takes over
+    KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, n_blobs), 1);
+    u -= mm.levels;
+  }
+  KL("merkle_top", launch_merkle_top(ctx->stream, mp.tree, mp.tree_stride, u, keep ? 1 : 0, roots, roots_stride, chan,
+                                     alpha, alpha_stride, n_blobs),
+     1);
+  return FRIEDA_OK;
+}
+
+// Merkle tree over layer `layer` of a wave: existing columns (layer 0) or the fused fold of the
+// previous layer.
 int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channel *chan, uint8_t *roots,
                 size_t roots_stride) {
   const Geom &g = pl.g;
@@ -323,31 +370,8 @@ int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channe
   }
   mp.tree = at<uint8_t>(ctx, pl.o_tree[layer]);
   mp.tree_stride = pl.tree_stride[layer];
-  mp.log = d;
-  mp.chunk_log = d < 10 ? d : 10;
-  mp.levels = mp.chunk_log;
-  mp.src_level = d;
-  mp.write_all = pl.keep ? 1 : 0;
-  KL(src == SRC_COLS ? "merkle_bottom_cols" : src == SRC_FOLD_CIRCLE ? "fold_circle+merkle_bottom" : "fold_line+merkle_bottom",
-     launch_merkle_bottom(ctx->stream, src, mp, pl.B), 1);
-  uint32_t u = d - mp.chunk_log;
-  while (u > 10) {
-    MerkleBottomParams mm = mp;
-    mm.src_cols = nullptr;
-    mm.dst_cols = nullptr;
-    mm.alpha = nullptr;
-    mm.log = u;
-    mm.src_level = u;
-    mm.chunk_log = (u - 10) < 10 ? (u - 10 < 1 ? 1 : u - 10) : 10;
-    mm.levels = mm.chunk_log;
-    KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, pl.B), 1);
-    u -= mm.chunk_log;
-  }
   QM31 *alpha = chan ? at<QM31>(ctx, pl.o_alpha) + layer : nullptr;
-  KL("merkle_top", launch_merkle_top(ctx->stream, mp.tree, mp.tree_stride, u, pl.keep ? 1 : 0, roots, roots_stride, chan, alpha,
-                       g.n_layers, pl.B),
-     1);
-  return FRIEDA_OK;
+  return run_tree(ctx, src, mp, d, pl.levels_cfg, pl.keep, pl.B, roots, roots_stride, chan, alpha, g.n_layers);
 }
 
 CPoint half_initial_point(const Geom &g) { return host::point_from_index(half_odds_index(g.D - 1, 0)); }
@@ -391,6 +415,7 @@ int commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride
   int rc = make_geom(ctx, len, log_blowup, pl.g);
   if (rc) return rc;
   pl.keep = false;
+  pl.levels_cfg = ctx->levels_for(n, pl.g.D);
   if (pl.g.D >= 3 && (rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, !device_io, 0);
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
@@ -478,6 +503,7 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
   if (rc) return rc;
   pl.fri = true;
   pl.keep = ctx->debug_keep;
+  pl.levels_cfg = ctx->levels_for(n, pl.g.D);
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, !device_io, 0);
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
@@ -535,6 +561,7 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   pl.fri = true;
   pl.prove = true;
   pl.keep = true;
+  pl.levels_cfg = ctx->levels_for(n, pl.g.D);
   const uint32_t nq = (uint32_t)cfg->n_queries;
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, true, nq);
@@ -714,6 +741,10 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
     delete ctx;
     return FRIEDA_ERR_CUDA;
   }
+  if (const char *ev = std::getenv("FRIEDA_MERKLE_LEVELS")) {
+    int v = std::atoi(ev);
+    if (v >= 1 && v <= 10) ctx->merkle_levels_big = (uint32_t)v;
+  }
   CPoint cur = {host::GEN_X, host::GEN_Y};
   for (int j = 0; j < 31; j++) {
     ctx->gp.g[j] = cur;
@@ -850,16 +881,72 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
 }
 
 // ---- split blob (config 5) ------------------------------------------------------------------
+// Rank `rank` of `world` = 2^g owns the bit-reversed-order index range [rank N/world, (rank+1) N/world)
+// of every column = the Merkle subtree (level g, index rank).  The circle FFT runs its largest
+// strides first, so that range is computable from the coefficient vector alone (launch_lde with an
+// owned range): no exchange of evaluations.  Only the 32-byte subtree roots travel (NCCL
+// all-gather in the host layer), then frieda_merkle_combine hashes the top g levels.
 int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
                               uint32_t world, uint8_t *d_subroot_out) {
   if (!ctx) return FRIEDA_ERR_ARG;
-  (void)data; (void)len; (void)log_blowup; (void)rank; (void)world; (void)d_subroot_out;
-  return ctx->fail_arg("frieda_commit_split_local: not implemented yet");
+  if ((!data && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
+  if (world == 0 || (world & (world - 1)) || rank >= world) return ctx->fail_arg("world must be a power of two > rank");
+  CU(cudaSetDevice(ctx->device));
+  Plan pl;
+  int rc = make_geom(ctx, len, log_blowup, pl.g);
+  if (rc) return rc;
+  const Geom &g = pl.g;
+  uint32_t gl = 0;
+  while ((1u << gl) < world) gl++;
+  if (gl > g.D) return ctx->fail_arg("more ranks than evaluation points");
+  const uint32_t rlog = g.D - gl;  // log size of the owned range
+  if (g.D < 3) return ctx->fail_arg("domain too small to split");
+  if (g.p > 15 && rlog < 14) return ctx->fail_arg("owned range too small for this polynomial size");
+  if ((rc = ensure_twiddles(ctx, g.D - 1))) return rc;
+  // workspace: staged input, coefficients, owned evaluations, truncated tree
+  Bump bp;
+  size_t o_in = bp.take(align_up(len ? len : 1, 16));
+  size_t o_coef = bp.take((size_t)16 << g.p);
+  size_t o_eval = bp.take((size_t)16 << rlog);
+  const uint32_t lv = ctx->levels_for(1, rlog);
+  size_t slots = tree_slots(rlog, false, lv);
+  size_t o_tree = bp.take(slots * 32);
+  if ((rc = ensure_arena(ctx, bp.off))) return rc;
+  ctx->have_last = false;
+  uint8_t *d_in = at<uint8_t>(ctx, o_in);
+  if (len) CU(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t *coef = at<uint32_t>(ctx, o_coef);
+  uint32_t *eval = at<uint32_t>(ctx, o_eval);
+  KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
+  LdeRange rg{(size_t)rank << rlog, rlog};
+  KL("lde", launch_lde(ctx->stream, coef, eval, g.p, g.beta, 1, g.n_felts, table(ctx), half_initial_point(g), &rg),
+     (g.p > 15 ? 2 : 1));
+  MerkleBottomParams mp;
+  std::memset(&mp, 0, sizeof mp);
+  mp.src_cols = eval;
+  mp.src_stride = (size_t)4 << rlog;
+  mp.tree = at<uint8_t>(ctx, o_tree);
+  mp.tree_stride = slots;
+  if ((rc = run_tree(ctx, SRC_COLS, mp, rlog, lv, false, 1, nullptr, 0, nullptr, nullptr, 0))) return rc;
+  CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return FRIEDA_OK;
 }
+
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]) {
   if (!ctx) return FRIEDA_ERR_ARG;
-  (void)d_subroots; (void)world; (void)root_out;
-  return ctx->fail_arg("frieda_merkle_combine: not implemented yet");
+  if (!d_subroots || !root_out) return ctx->fail_arg("null pointer");
+  if (world == 0 || (world & (world - 1)) || world > 64) return ctx->fail_arg("world must be a power of two <= 64");
+  CU(cudaSetDevice(ctx->device));
+  uint32_t gl = 0;
+  while ((1u << gl) < world) gl++;
+  // scratch tree (heap order): the subtree roots are level gl; d_scratch holds 2 * 64 slots
+  uint8_t *tree = ctx->d_scratch;
+  CU(cudaMemcpyAsync(tree + (size_t)world * 32, d_subroots, (size_t)world * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  KL("merkle_top", launch_merkle_top(ctx->stream, tree, 2 * (size_t)world, gl, 0, nullptr, 0, nullptr, nullptr, 0, 1), 1);
+  CU(cudaMemcpyAsync(root_out, tree + 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return FRIEDA_OK;
 }
 
 // ---- standalone passes ------------------------------------------------------------------------
@@ -896,7 +983,8 @@ int frieda_pass_merkle(frieda_ctx *ctx, const uint32_t *d_cols, uint32_t log, si
   CU(cudaSetDevice(ctx->device));
   if (log > 28) return ctx->fail_arg("bad tree size");
   const bool keep = d_tree != nullptr;
-  size_t slots = tree_slots(log, keep);
+  const uint32_t lv = ctx->levels_for(n, log);
+  size_t slots = tree_slots(log, keep, lv);
   uint8_t *tree = d_tree;
   if (!keep) {
     int rc = ensure_arena(ctx, n * slots * 32 + 256);
@@ -910,25 +998,8 @@ int frieda_pass_merkle(frieda_ctx *ctx, const uint32_t *d_cols, uint32_t log, si
   mp.src_stride = (size_t)4 << log;
   mp.tree = tree;
   mp.tree_stride = slots;
-  mp.log = log;
-  mp.chunk_log = log < 10 ? log : 10;
-  mp.levels = mp.chunk_log;
-  mp.src_level = log;
-  mp.write_all = keep;
-  KL("merkle_bottom_cols", launch_merkle_bottom(ctx->stream, SRC_COLS, mp, n), 1);
-  uint32_t u = log - mp.chunk_log;
-  while (u > 10) {
-    MerkleBottomParams mm = mp;
-    mm.src_cols = nullptr;
-    mm.log = u;
-    mm.src_level = u;
-    mm.chunk_log = (u - 10) < 10 ? u - 10 : 10;
-    mm.levels = mm.chunk_log;
-    KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, n), 1);
-    u -= mm.chunk_log;
-  }
-  // roots land in an aligned staging area first (caller pointers may be unaligned)
-  KL("merkle_top", launch_merkle_top(ctx->stream, tree, slots, u, keep, nullptr, 0, nullptr, nullptr, 0, n), 1);
+  int rc2 = run_tree(ctx, SRC_COLS, mp, log, lv, keep, n, nullptr, 0, nullptr, nullptr, 0);
+  if (rc2) return rc2;
   CU(cudaMemcpy2DAsync(d_roots, 32, tree + 32, slots * 32, 32, n, cudaMemcpyDeviceToDevice, ctx->stream));
   return FRIEDA_OK;
 }

@@ -16,7 +16,7 @@ constexpr int GR_THREADS = 256;
 constexpr uint32_t GR_CTA_LOG = 14;  // nonces per CTA
 
 __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__restrict__ chan, uint32_t pow_bits,
-                                                           uint64_t base, unsigned long long *best) {
+                                                           uint64_t base, unsigned long long *best, uint32_t one) {
   const size_t blob = blockIdx.y;
   const uint64_t start = base + ((uint64_t)blockIdx.x << GR_CTA_LOG);
   volatile unsigned long long *vb = best + blob;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__rest
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = d[i];
     uint32_t m[16] = {(uint32_t)nonce, (uint32_t)(nonce >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    blake2s_compress(h, m, 0, 0, 0, 0);
+    blake2s_compress_t<0x0003u>(h, m, 0, 0, 0, 0, one);  // only the two nonce words are non-zero
     if (digest_trailing_zeros(h) >= pow_bits) {
       atomicMin(best + blob, (unsigned long long)nonce);
       break;  // later nonces of this thread are larger
@@ -45,7 +45,7 @@ cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits
   unsigned chunks = 1u << (range_log - GR_CTA_LOG);
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
-    grind_kernel<<<dim3(chunks, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, base, best + b0);
+    grind_kernel<<<dim3(chunks, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, base, best + b0, 1u);
   }
   return cudaGetLastError();
 }

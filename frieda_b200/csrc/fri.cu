@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
     // leaves
     for (uint32_t j = tid; j < n; j += TAIL_THREADS) {
       uint32_t h[8];
-      merkle_hash_leaf(s_cols[cur][0][j], s_cols[cur][1][j], s_cols[cur][2][j], s_cols[cur][3][j], h);
+      merkle_hash_leaf(s_cols[cur][0][j], s_cols[cur][1][j], s_cols[cur][2][j], s_cols[cur][3][j], h, p.one);
       t_store(&s_ha[j], h);
       if (p.write_all || log == 0) t_store(tree + n + j, h);
     }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
       for (uint32_t j = tid; j < cnt; j += TAIL_THREADS) {
         uint32_t m[16], h[8];
         t_load_pair(hc + 2 * j, m);
-        merkle_hash_node(m, h);
+        merkle_hash_node(m, h, p.one);
         t_store(&hn[j], h);
         if (p.write_all || level == 1) t_store(tree + cnt + j, h);
       }
@@ -146,12 +146,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
     // fold into the next layer
     const uint32_t nn = n >> 1;
     uint32_t *dst = p.cols[layer + 1] + blob * p.cols_stride[layer + 1];
-    if (layer == 0 && log <= 2) {
-      // tiny circle domains (D = 1, 2) have no twiddle table entry: p = domain.at(brev(2i, D)),
-      // recomputed from the half coset's initial point carried in inv_last_n's neighbour fields
-      // is not needed here -- such inputs are rejected by the host (poly_log - 1 >= log_last
-      // forces D >= 1 + log_blowup; D <= 2 only with tiny blowups, handled by launch_fold's caller).
-    }
+    // (circle domains below 8 points are rejected by the host: make_geom_fri)
     const uint32_t *iblk = layer == 0 ? p.tt.iblk(1u << (log - 2)) : p.tt.iblk(1u << (log - 1));
     for (uint32_t i = tid; i < nn; i += TAIL_THREADS) {
       QM31 a = {{s_cols[cur][0][2 * i], s_cols[cur][1][2 * i], s_cols[cur][2][2 * i], s_cols[cur][3][2 * i]}};
@@ -207,10 +202,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
     }
   }
   __syncthreads();
-  __threadfence_block();
   if (tid == 0) {
     // mix_felts(last_layer_poly); the coefficients were just written by this CTA
-    __threadfence();
     channel_mix_felts(ch, p.last_poly + blob * bound, bound);
     p.chan[blob] = ch;
   }
@@ -221,6 +214,7 @@ cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs) {
   for (size_t b0 = 0; b0 < n_blobs; b0 += 65535) {
     size_t nb = n_blobs - b0 < 65535 ? n_blobs - b0 : 65535;
     TailParams q = p;
+    q.one = 1u;
     for (int l = 0; l < 32; l++) {
       if (q.cols[l]) q.cols[l] += b0 * p.cols_stride[l];
       if (q.tree[l]) q.tree[l] += b0 * p.tree_stride[l] * 32;

@@ -50,14 +50,22 @@ struct MerkleBottomParams {
   uint32_t levels;           // levels reduced inside the CTA (<= chunk_log)
   uint32_t src_level;        // SRC_NODES: tree level the 2^log input nodes live on; others: == log
   int write_all;             // write every level (leaves included) to the tree, not only the tops
+  uint32_t one;              // runtime 1 for the IMAD adds of the compression (blake2s.cuh); set by the launcher
 };
 
 cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
                         uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
 cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw);
-// Circle-FFT low-degree extension of n_blobs x 4 coefficient columns.
+// Owned slice of the evaluation domain (bit-reversed order): [lo, lo + 2^log); lo is a
+// multiple of 2^log.  The evaluation buffer then holds 4 x 2^log words per blob.
+struct LdeRange {
+  size_t lo;
+  uint32_t log;
+};
+// Circle-FFT low-degree extension of n_blobs x 4 coefficient columns (range == nullptr: all).
 cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t poly_log, uint32_t log_blowup,
-                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial);
+                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial,
+                       const LdeRange *range = nullptr);
 cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomParams &p, size_t n_blobs);
 // One CTA per blob: reduce 2^top_log nodes at tree level top_log to the root; optionally
 // mix_root + draw the folding alpha on the blob's channel.
@@ -89,6 +97,7 @@ struct TailParams {
   QM31 *last_poly;      // [blob][2^log_last]
   int *error_flag;      // set to 1 on "invalid degree"
   TwiddleTable tt;
+  uint32_t one;         // runtime 1 (blake2s.cuh); set by the launcher
 };
 constexpr uint32_t TAIL_LOG = 9;      // layers with log <= TAIL_LOG are finished by the tail kernel
 constexpr uint32_t TAIL_LAST_MAX = 9; // largest supported log_last + log_blowup

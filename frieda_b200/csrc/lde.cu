@@ -106,22 +106,28 @@ cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, ui
 // Columns whose coefficients are all zero evaluate to zero; layers whose upper inputs are all
 // zero (coefficient prefix shorter than the stride) are replications.  Both are arithmetic
 // identities, not special-casing of a config.
+// `rg` restricts the output to the owned index range [lo, lo + 2^log) (split-blob path): whole
+// blocks when the range is at least a block, otherwise the in-range part of one block.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *__restrict__ coef,
                                                             uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
-                                                            uint32_t n_felts, TwiddleTable tt) {
+                                                            uint32_t n_felts, TwiddleTable tt, LdeRange rg) {
   extern __shared__ uint32_t sm[];
-  const uint32_t hb = blockIdx.x, col = blockIdx.y;
+  const uint32_t hb = blockIdx.x + (uint32_t)(rg.lo >> p), col = blockIdx.y;
   const size_t blob = blockIdx.z;
   const uint32_t n4 = 1u << p;
   const uint32_t D = p + beta, K = D - 1;
   const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
-  uint32_t *out = eval + ((blob * 4 + col) << D) + ((size_t)hb << p);
+  // local window of this block inside the owned range
+  const uint32_t w_lo = rg.log >= p ? 0u : (uint32_t)(rg.lo & (n4 - 1));
+  const uint32_t w_n = rg.log >= p ? n4 : (1u << rg.log);
+  // out[i], i = index inside the block, addresses the owned-range buffer (global index - rg.lo)
+  uint32_t *out = eval + ((blob * 4 + col) << rg.log) + ((ptrdiff_t)((size_t)hb << p) - (ptrdiff_t)rg.lo);
   // non-zero prefix of this column
   uint32_t first = col * n4;
   uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
   if (nz == 0) {
-    for (uint32_t i = threadIdx.x; i < n4; i += THREADS) out[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
     return;
   }
   // m = ceil(log2(nz)): layers i >= m only replicate
@@ -156,10 +162,16 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *__re
       uint2 v = reinterpret_cast<const uint2 *>(sm)[bf];
       uint32_t tmp = m31_mul(v.y, t);
       uint2 r = {m31_add(v.x, tmp), m31_sub(v.x, tmp)};
-      reinterpret_cast<uint2 *>(out)[bf] = r;
+      if (w_n == n4) {
+        reinterpret_cast<uint2 *>(out)[bf] = r;
+      } else {
+        const uint32_t i0 = 2 * bf;
+        if (i0 >= w_lo && i0 < w_lo + w_n) out[i0] = r.x;
+        if (i0 + 1 >= w_lo && i0 + 1 < w_lo + w_n) out[i0 + 1] = r.y;
+      }
     }
   } else {
-    for (uint32_t i = threadIdx.x; i < n4; i += THREADS) out[i] = sm[i];
+    for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = sm[w_lo + i];
   }
 }
 
@@ -197,7 +209,7 @@ template <int THREADS, bool FIRST>
 __global__ void __launch_bounds__(THREADS) lde_strided_kernel(const uint32_t *__restrict__ coef,
                                                               uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
                                                               uint32_t n_felts, uint32_t top, uint32_t r, uint32_t w,
-                                                              TwiddleTable tt) {
+                                                              TwiddleTable tt, LdeRange rg) {
   // handles layers top-1 .. top-r of every 2^top-point sub-FFT; rows are 2^(top-r) apart
   extern __shared__ uint32_t sm[];
   const uint32_t D = p + beta, K = D - 1;
@@ -205,11 +217,14 @@ __global__ void __launch_bounds__(THREADS) lde_strided_kernel(const uint32_t *__
   const size_t blob = blockIdx.z;
   const uint32_t row_stride_log = top - r;                 // distance between rows (log)
   const uint32_t tiles_per_sub = 1u << (row_stride_log - w);  // tiles inside one sub-FFT
-  const uint32_t sub = blockIdx.x / tiles_per_sub;         // which 2^top-point sub-FFT (global index)
+  // which 2^top-point sub-FFT (global index); only those touching the owned range are launched
+  const uint32_t sub = blockIdx.x / tiles_per_sub + (uint32_t)(rg.lo >> top);
   const uint32_t tile = blockIdx.x % tiles_per_sub;
   const size_t base = ((size_t)sub << top) + ((size_t)tile << w);
   const uint32_t n4 = 1u << p;
-  uint32_t *ev = eval + ((blob * 4 + col) << D);
+  // evaluations are stored for the owned range only: local address = global index - rg.lo
+  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) - rg.lo;
+  const size_t rg_hi = rg.lo + ((size_t)1 << rg.log);
   const uint32_t rows = 1u << r, cols = 1u << w;
   uint32_t first = col * n4;
   uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
@@ -248,20 +263,21 @@ __global__ void __launch_bounds__(THREADS) lde_strided_kernel(const uint32_t *__
   }
   for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
     uint32_t row = e >> w, cc = e & (cols - 1);
-    ev[base + ((size_t)row << row_stride_log) + cc] = sm[e];
+    size_t idx = base + ((size_t)row << row_stride_log) + cc;
+    if (idx >= rg.lo && idx < rg_hi) ev[idx] = sm[e];
   }
 }
 
 // Contiguous chunk pass, in place on the evaluations: layers c-1 .. 0 of every 2^c chunk.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) lde_chunk_kernel(uint32_t *__restrict__ eval, uint32_t D, uint32_t c,
-                                                            TwiddleTable tt) {
+                                                            TwiddleTable tt, LdeRange rg) {
   extern __shared__ uint32_t sm[];
   const uint32_t K = D - 1;
   const uint32_t col = blockIdx.y;
   const size_t blob = blockIdx.z;
-  const size_t chunk = blockIdx.x;
-  uint32_t *ev = eval + ((blob * 4 + col) << D) + (chunk << c);
+  const size_t chunk = blockIdx.x + (rg.lo >> c);  // global chunk index
+  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) + ((size_t)blockIdx.x << c);
   const uint32_t n = 1u << c;
   for (uint32_t i = threadIdx.x; i < n; i += THREADS) sm[i] = ev[i];
   __syncthreads();
@@ -295,10 +311,14 @@ __global__ void __launch_bounds__(THREADS) lde_chunk_kernel(uint32_t *__restrict
 constexpr uint32_t LDE_SMEM_LOG_MAX = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
 
 cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t p, uint32_t beta,
-                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial) {
+                       size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial,
+                       const LdeRange *range) {
   const uint32_t D = p + beta;
   if (D == 0) return cudaErrorInvalidValue;
+  LdeRange rg = range ? *range : LdeRange{0, D};
+  if (rg.log > D || (rg.lo & (((size_t)1 << rg.log) - 1)) || rg.lo >= ((size_t)1 << D)) return cudaErrorInvalidValue;
   if (D <= 2) {
+    if (rg.log != D) return cudaErrorInvalidValue;
     size_t n_cols = n_blobs * 4;
     lde_tiny_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(coef, eval, p, D, n_cols, half_initial);
     return cudaGetLastError();
@@ -315,38 +335,46 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
     const uint32_t *cf = coef + b0 * ((size_t)4 << p);
-    uint32_t *ev = eval + b0 * ((size_t)4 << D);
+    uint32_t *ev = eval + b0 * ((size_t)4 << rg.log);
     if (p <= LDE_SMEM_LOG_MAX) {
-      dim3 grid(1u << beta, 4, (unsigned)nb);
+      dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
       size_t smem = (size_t)4 << p;
       if (p >= 11)
-        lde_block_kernel<1024><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, tt);
+        lde_block_kernel<1024><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, tt, rg);
       else
-        lde_block_kernel<256><<<grid, 256, smem, st>>>(cf, ev, p, beta, n_felts, tt);
+        lde_block_kernel<256><<<grid, 256, smem, st>>>(cf, ev, p, beta, n_felts, tt, rg);
     } else {
       // strided passes over layers p-1 .. c, then contiguous chunks of 2^c; every tile is
-      // 2^14 words (64 KiB) with rows of at least 2^5 consecutive words (128 B)
+      // 2^14 words (64 KiB) with rows of at least 2^5 consecutive words (128 B).  The first
+      // pass reads the coefficients, so it may compute more rows than the owned range keeps;
+      // it is made deep enough that every later pass stays inside the owned range.
       const uint32_t c = 14;
+      if (rg.log < c) return cudaErrorInvalidValue;
       const uint32_t n_passes = (p - c + 8) / 9;
       uint32_t top = p;
       bool firstpass = true;
       for (uint32_t pass = 0; pass < n_passes; pass++) {
         uint32_t left = n_passes - pass;
         uint32_t r = (top - c + left - 1) / left;
+        if (firstpass && rg.log < top && top - rg.log > r) r = top - rg.log;
+        if (r > 9) return cudaErrorInvalidValue;
         uint32_t w = 14 - r;
-        uint32_t subs = 1u << (D - top);
+        // sub-FFTs of 2^top points touching the range
+        uint32_t subs = rg.log >= top ? 1u << (rg.log - top) : 1u;
         uint32_t tiles = subs << (top - r - w);
         dim3 grid(tiles, 4, (unsigned)nb);
         size_t smem = (size_t)4 << (r + w);
         if (firstpass)
-          lde_strided_kernel<1024, true><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt);
+          lde_strided_kernel<1024, true><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt, rg);
         else
-          lde_strided_kernel<1024, false><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt);
+          lde_strided_kernel<1024, false><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt, rg);
         firstpass = false;
         top -= r;
+        if (top == c) break;
       }
-      dim3 grid(1u << (D - c), 4, (unsigned)nb);
-      lde_chunk_kernel<1024><<<grid, 1024, (size_t)4 << c, st>>>(ev, D, c, tt);
+      if (top != c) return cudaErrorInvalidValue;
+      dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
+      lde_chunk_kernel<1024><<<grid, 1024, (size_t)4 << c, st>>>(ev, D, c, tt, rg);
     }
   }
   return cudaGetLastError();

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleB
         d[3 * n] = c3;
       }
       uint32_t h[8];
-      merkle_hash_leaf(c0, c1, c2, c3, h);
+      merkle_hash_leaf(c0, c1, c2, c3, h, p.one);
       store_hash(&sm_a[j], h);
       if (p.write_all) store_hash(tree + n + i, h);
     }
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleB
     for (uint32_t j = threadIdx.x; j < cnt; j += MB_THREADS) {
       uint32_t m[16], h[8];
       load_pair(cur + 2 * j, m);
-      merkle_hash_node(m, h);
+      merkle_hash_node(m, h, p.one);
       store_hash(&nxt[j], h);
       if (p.write_all || top) store_hash(tree + ((size_t)1 << level) + idx0 + j, h);
     }
@@ -130,6 +130,7 @@ cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomPar
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
     MerkleBottomParams q = p;
+    q.one = 1u;
     if (q.src_cols) q.src_cols += b0 * p.src_stride;
     if (q.dst_cols) q.dst_cols += b0 * p.dst_stride;
     q.tree += b0 * p.tree_stride * 32;
@@ -155,7 +156,8 @@ constexpr uint32_t MT_TOP_LOG_MAX = 10;
 
 __global__ void __launch_bounds__(MT_THREADS) merkle_top_kernel(uint8_t *tree_, size_t tree_stride, uint32_t top_log,
                                                                  int write_all, uint8_t *roots, size_t roots_stride,
-                                                                 Channel *chan, QM31 *alpha, size_t alpha_stride) {
+                                                                 Channel *chan, QM31 *alpha, size_t alpha_stride,
+                                                                 uint32_t one) {
   __shared__ Hash32 sm_a[1u << MT_TOP_LOG_MAX];
   __shared__ Hash32 sm_b[1u << (MT_TOP_LOG_MAX - 1)];
   const size_t blob = blockIdx.x;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(MT_THREADS) merkle_top_kernel(uint8_t *tree_, 
     for (uint32_t j = threadIdx.x; j < cnt; j += MT_THREADS) {
       uint32_t m[16], h[8];
       load_pair(cur + 2 * j, m);
-      merkle_hash_node(m, h);
+      merkle_hash_node(m, h, one);
       store_hash(&nxt[j], h);
       if (write_all || level == 1) store_hash(tree + cnt + j, h);
     }
@@ -197,7 +199,7 @@ cudaError_t launch_merkle_top(cudaStream_t st, uint8_t *tree, size_t tree_stride
                               size_t n_blobs) {
   if (top_log > MT_TOP_LOG_MAX) return cudaErrorInvalidValue;
   merkle_top_kernel<<<(unsigned)n_blobs, MT_THREADS, 0, st>>>(tree, tree_stride, top_log, write_all, roots,
-                                                              roots_stride, chan, alpha, alpha_stride);
+                                                              roots_stride, chan, alpha, alpha_stride, 1u);
   return cudaGetLastError();
 }
 

@@ -500,3 +500,41 @@ def test_prove_batch_in_waves(ctx):
     for b in range(n):
         oroot, opr = O.prove(blobs[b].tobytes(), seeds[b], O.make_config(*cfg))
         assert roots[b].tobytes() == oroot and proofs[b].serialize() == opr.serialize(), b
+
+
+# ------------------------------------------------------------------ split blob (BASELINE config 5)
+@pytest.mark.parametrize("n_bytes,blow,worlds", [
+    (1 << 20, 2, (1, 2, 4, 8)),      # poly_log 17: strided LDE passes; world 8 > 2^blowup -> partial blocks
+    (131072, 1, (2, 4)),             # shared-memory LDE path with a partial block
+    (131072, 4, (1, 2, 8, 16)),      # whole blocks per rank
+    (3000, 3, (2, 16)),
+])
+def test_commit_split_virtual_ranks(ctx, torch_mod, n_bytes, blow, worlds):
+    # sharding logic on ONE GPU: G virtual ranks run sequentially, subtree roots are combined,
+    # and the result must equal the unsplit commit (and the oracle)
+    torch = torch_mod
+    data = O.splitmix64_bytes(0x4652494544414236, n_bytes)
+    want = O.commit(data, blow)
+    assert ctx.commit(data, blow) == want
+    for world in worlds:
+        subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            ctx.commit_split_local(data, blow, r, world, subs[r].data_ptr())
+        assert ctx.merkle_combine(subs.data_ptr(), world) == want, world
+
+
+def test_commit_split_single_process_api(ctx):
+    from frieda_b200.parallel import commit_split
+    data = pattern(50000)
+    assert commit_split(ctx, data, 3) == O.commit(data, 3)
+
+
+def test_commit_split_subroots_are_tree_nodes(ctx, torch_mod):
+    torch = torch_mod
+    data = pattern(20000)
+    t = O.trace(data, None, O.make_config(2, 0, 4, 1), stop_after_fri=True, with_trees=True)
+    world = 4
+    subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+    for r in range(world):
+        ctx.commit_split_local(data, 2, r, world, subs[r].data_ptr())
+    assert subs.cpu().numpy().tobytes() == t.tree_levels[0][2].tobytes()

@@ -1,0 +1,77 @@
+"""Host-side multi-GPU logic on CPU: blob sharding, and the subtree-root exchange of the split-blob
+path over a world_size-2 gloo group (the CUDA ranks use the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from frieda_b200 import parallel
+from oracle import oracle as O
+
+
+def test_shard_blobs_partitions_exactly():
+    for n in (0, 1, 7, 4096, 4099):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_blobs(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0
+            assert sum(c for _, c in spans) == n
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_blobs(4, 4, 4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, level_nodes, root_hex, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # each rank contributes "its" subtree root (precomputed by the oracle for this test)
+        sub = torch.from_numpy(np.frombuffer(level_nodes[rank], dtype=np.uint8).copy())
+        gathered = parallel.all_gather_roots(sub)
+        got = gathered.numpy().tobytes()
+        ok = got == b"".join(level_nodes)
+        # top levels over the gathered roots with the oracle's compression (checker side)
+        level = [np.frombuffer(x, dtype="<u4") for x in level_nodes]
+        while len(level) > 1:
+            level = [np.array(O.blake2s_compress([0] * 8, [int(v) for v in level[2 * i]] + [int(v) for v in
+                                                                                            level[2 * i + 1]]),
+                              dtype="<u4") for i in range(len(level) // 2)]
+        ok = ok and level[0].tobytes().hex() == root_hex
+        start, count = parallel.shard_blobs(4096, rank, world)
+        ok = ok and (start, count) == (rank * 2048, 2048)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_subtree_root_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    data = bytes(i % 256 for i in range(20000))
+    t = O.trace(data, None, O.make_config(2, 0, 4, 1), stop_after_fri=True, with_trees=True)
+    world = 2
+    nodes = [t.tree_levels[0][1][r].tobytes() for r in range(world)]
+    root_hex = t.tree_levels[0][0].tobytes().hex()
+    assert root_hex == O.commit(data, 2).hex()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, nodes, root_hex, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
