@@ -100,79 +100,194 @@ cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, ui
 }
 
 // ---------------------------------------------------------------- LDE
-// One CTA = one (block hb, column, blob): 2^p-point FFT in shared memory, layers p-1 .. 0.
+// One CTA = one (block hb, column, blob): a 2^p-point FFT, layers p-1 .. 0, done as radix-16
+// passes held in registers (4 layers per shared-memory round trip) and a last pass of
+// R_last = ((p-1) mod 4) + 1 layers over 2^R_last consecutive points whose results go straight to
+// HBM as 128-bit stores.  The first pass reads the coefficients straight from global memory
+// (coalesced: consecutive threads take consecutive low index bits).
 // Layer i >= 1 (line): twiddle = blk(2^(K-i))[idx >> (i+1)];  layer 0 (circle): from the pairs
 // (x, y) of blk(2^(K-1)) as [y, -y, -x, x] (stwo circle_twiddles_from_line_twiddles).
-// Columns whose coefficients are all zero evaluate to zero; layers whose upper inputs are all
-// zero (coefficient prefix shorter than the stride) are replications.  Both are arithmetic
-// identities, not special-casing of a config.
+// A column whose coefficients are all zero evaluates to zero (an arithmetic identity, not a
+// special case of a config).  Shared memory carries 4 pad words per 64 so that the pass whose
+// stride is below a warp's width stays bank-conflict free.
 // `rg` restricts the output to the owned index range [lo, lo + 2^log) (split-blob path): whole
 // blocks when the range is at least a block, otherwise the in-range part of one block.
-template <int THREADS>
+__device__ __forceinline__ uint32_t padi(uint32_t i) { return i + ((i >> 6) << 2); }
+
+__device__ __forceinline__ void bfly_t2(uint32_t &a, uint32_t &b, uint32_t t2) {
+  uint32_t tmp = m31_mul_t2(b, t2), va = a;
+  a = m31_add(va, tmp);
+  b = m31_sub(va, tmp);
+}
+
+// R line layers top, top-1, .. top-R+1 over the 2^R register values v[j]; element j has global
+// index base + (j << lo) with lo = top - R + 1, and `tw_row(i)` = twiddle row of layer i already
+// offset to this group (index of element 0 >> (i+1)).
+template <int R, int NSTAGES>
+__device__ __forceinline__ void line_stages(uint32_t (&v)[1 << R], const TwiddleTable &tt, uint32_t K, uint32_t p,
+                                            uint32_t hb, uint32_t top, uint32_t grp_hi) {
+#pragma unroll
+  for (int s = 0; s < NSTAGES; s++) {
+    const uint32_t i = top - s;
+    const uint32_t *tw = tt.blk(1u << (K - i)) + ((size_t)hb << (p - i - 1)) + ((size_t)grp_hi << s);
+    constexpr int N = 1 << R;
+    const int half = N >> (s + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << s); g++) {
+      uint32_t t = __ldg(tw + g);
+      uint32_t t2 = t + t;
+#pragma unroll
+      for (int k = 0; k < half; k++) bfly_t2(v[g * 2 * half + k], v[g * 2 * half + k + half], t2);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void last_pass(const uint32_t *__restrict__ src, bool src_is_smem, uint32_t *__restrict__ out,
+                                          uint32_t g, const TwiddleTable &tt, uint32_t K, uint32_t p, uint32_t hb,
+                                          uint32_t w_lo, uint32_t w_n, bool full) {
+  constexpr int N = 1 << R;
+  uint32_t v[N];
+  const uint32_t idx0 = g << R;
+  if (src_is_smem) {
+    if (R >= 2) {
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        uint4 q = *reinterpret_cast<const uint4 *>(src + padi(idx0 + j));
+        v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+      }
+    } else {
+      uint2 q = *reinterpret_cast<const uint2 *>(src + padi(idx0));
+      v[0] = q.x; v[1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = __ldg(src + idx0 + j);
+  }
+  // line layers R-1 .. 1
+  line_stages<R, R - 1>(v, tt, K, p, hb, R - 1, g);
+  // circle layer
+  {
+    const uint32_t *tw0 = tt.blk(1u << (K - 1));
+    const uint32_t h_base = (hb << (p - 1)) + (g << (R - 1));
+#pragma unroll
+    for (int jj = 0; jj < N / 2; jj++) {
+      uint32_t h = h_base + jj;
+      uint32_t q = h >> 2, e = h & 3;
+      uint32_t x = __ldg(tw0 + 2 * q), y = __ldg(tw0 + 2 * q + 1);
+      uint32_t t = e == 0 ? y : e == 1 ? m31_neg(y) : e == 2 ? m31_neg(x) : x;
+      bfly_t2(v[2 * jj], v[2 * jj + 1], t + t);
+    }
+  }
+  if (full) {
+    if (R >= 2) {
+#pragma unroll
+      for (int j = 0; j < N; j += 4)
+        *reinterpret_cast<uint4 *>(out + idx0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      *reinterpret_cast<uint2 *>(out + idx0) = make_uint2(v[0], v[1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      uint32_t i = idx0 + j;
+      if (i >= w_lo && i < w_lo + w_n) out[i] = v[j];
+    }
+  }
+}
+
+// One radix-16 pass over layers LO+3 .. LO with every index compile-time: the 16 shared-memory
+// slots of a group are one computed address plus immediates.
+template <int P, int LO, bool FROM_GLOBAL, int THREADS>
+__device__ __forceinline__ void r16_pass(const uint32_t *__restrict__ c, uint32_t *sm, const TwiddleTable &tt,
+                                         uint32_t K, uint32_t hb) {
+  // twiddle rows of the 4 layers, offset to this block (warp-uniform)
+  const uint32_t *row[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int i = LO + 3 - s;
+    row[s] = tt.blk(1u << (K - i)) + ((size_t)hb << (P - i - 1));
+  }
+  // padded offset of element j from element 0: the group's low bits never carry into bit 6
+  auto off = [](int j) -> uint32_t { return ((uint32_t)j << LO) + ((((uint32_t)j << LO) >> 6) << 2); };
+#pragma unroll 1
+  for (uint32_t g = threadIdx.x; g < (1u << (P - 4)); g += THREADS) {
+    const uint32_t lower = g & ((1u << LO) - 1), upper = g >> LO;
+    const uint32_t base = (upper << (LO + 4)) | lower;
+    uint32_t *slot = sm + padi(base);
+    uint32_t v[16];
+    if (FROM_GLOBAL) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) v[j] = __ldg(c + base + ((uint32_t)j << LO));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j++) v[j] = slot[off(j)];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const uint32_t *tw = row[s] + ((size_t)upper << s);
+      const int half = 8 >> s;
+#pragma unroll
+      for (int q = 0; q < (1 << s); q++) {
+        uint32_t t = __ldg(tw + q);
+        uint32_t t2 = t + t;
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) slot[off(j)] = v[j];
+  }
+}
+
+template <int P, int THREADS>
 __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *__restrict__ coef,
-                                                            uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
+                                                            uint32_t *__restrict__ eval, uint32_t beta,
                                                             uint32_t n_felts, TwiddleTable tt, LdeRange rg) {
-  extern __shared__ uint32_t sm[];
+  extern __shared__ __align__(16) uint32_t sm[];
+  constexpr uint32_t p = P;
   const uint32_t hb = blockIdx.x + (uint32_t)(rg.lo >> p), col = blockIdx.y;
   const size_t blob = blockIdx.z;
-  const uint32_t n4 = 1u << p;
+  constexpr uint32_t n4 = 1u << P;
   const uint32_t D = p + beta, K = D - 1;
   const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
   // local window of this block inside the owned range
   const uint32_t w_lo = rg.log >= p ? 0u : (uint32_t)(rg.lo & (n4 - 1));
   const uint32_t w_n = rg.log >= p ? n4 : (1u << rg.log);
+  const bool full = w_n == n4;
   // out[i], i = index inside the block, addresses the owned-range buffer (global index - rg.lo)
   uint32_t *out = eval + ((blob * 4 + col) << rg.log) + ((ptrdiff_t)((size_t)hb << p) - (ptrdiff_t)rg.lo);
-  // non-zero prefix of this column
-  uint32_t first = col * n4;
-  uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
-  if (nz == 0) {
+  if (n_felts <= col * n4) {  // all-zero column
     for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
     return;
   }
-  // m = ceil(log2(nz)): layers i >= m only replicate
-  uint32_t m = nz > 1 ? 32 - __clz(nz - 1) : 0;
-  const uint32_t mask = (1u << m) - 1;
-  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) {
-    uint32_t j = i & mask;
-    sm[i] = j < nz ? c[j] : 0u;
-  }
-  __syncthreads();
-  const uint32_t half = n4 >> 1;
-  for (int i = (int)m - 1; i >= 1; i--) {
-    const uint32_t *tw = tt.blk(1u << (K - i)) + ((size_t)hb << (p - i - 1));
-    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-      uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
-      uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
-      uint32_t t = __ldg(tw + hi);
-      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
-      sm[a] = m31_add(va, tmp);
-      sm[b] = m31_sub(va, tmp);
-    }
+  constexpr int R_LAST = ((P - 1) & 3) + 1;
+  constexpr int N_R16 = (P - R_LAST) >> 2;
+  if (N_R16 >= 1) {
+    r16_pass<P, (P >= 4 ? P - 4 : 0), true, THREADS>(c, sm, tt, K, hb);
     __syncthreads();
   }
-  if (m >= 1) {
-    // circle layer; results go straight to HBM
-    const uint32_t *tw = tt.blk(1u << (K - 1));
-    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-      uint32_t h = (hb << (p - 1)) | bf;
-      uint32_t q = h >> 2, e = h & 3;
-      uint32_t x = __ldg(tw + 2 * q), y = __ldg(tw + 2 * q + 1);
-      uint32_t t = e == 0 ? y : e == 1 ? m31_neg(y) : e == 2 ? m31_neg(x) : x;
-      uint2 v = reinterpret_cast<const uint2 *>(sm)[bf];
-      uint32_t tmp = m31_mul(v.y, t);
-      uint2 r = {m31_add(v.x, tmp), m31_sub(v.x, tmp)};
-      if (w_n == n4) {
-        reinterpret_cast<uint2 *>(out)[bf] = r;
-      } else {
-        const uint32_t i0 = 2 * bf;
-        if (i0 >= w_lo && i0 < w_lo + w_n) out[i0] = r.x;
-        if (i0 + 1 >= w_lo && i0 + 1 < w_lo + w_n) out[i0 + 1] = r.y;
-      }
-    }
-  } else {
-    for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = sm[w_lo + i];
+  if (N_R16 >= 2) {
+    r16_pass<P, (P >= 8 ? P - 8 : 0), false, THREADS>(c, sm, tt, K, hb);
+    __syncthreads();
   }
+  if (N_R16 >= 3) {
+    r16_pass<P, (P >= 12 ? P - 12 : 0), false, THREADS>(c, sm, tt, K, hb);
+    __syncthreads();
+  }
+  const uint32_t *src = N_R16 ? sm : c;
+#pragma unroll 1
+  for (uint32_t g = threadIdx.x; g < (n4 >> R_LAST); g += THREADS)
+    last_pass<R_LAST>(src, N_R16 != 0, out, g, tt, K, p, hb, w_lo, w_n, full);
+}
+
+// poly_log 0: one coefficient per column; every layer is a replication.
+__global__ void lde_copy_kernel(const uint32_t *__restrict__ coef, uint32_t *__restrict__ eval, uint32_t beta,
+                                uint32_t n_felts, LdeRange rg) {
+  const uint32_t hb = blockIdx.x + (uint32_t)rg.lo, col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  (void)beta;
+  eval[((blob * 4 + col) << rg.log) + (hb - rg.lo)] = n_felts > col ? coef[blob * 4 + col] : 0u;
 }
 
 // D == 1 and D == 2: stwo hard-codes these; one thread per (blob, column).
@@ -325,8 +440,11 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(lde_block_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
-    cudaFuncSetAttribute(lde_block_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
+    const int big = (4 << LDE_SMEM_LOG_MAX) + (4 << LDE_SMEM_LOG_MAX) / 16 + 64;
+    cudaFuncSetAttribute(lde_block_kernel<12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<13, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<14, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_strided_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
     cudaFuncSetAttribute(lde_strided_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
     cudaFuncSetAttribute(lde_chunk_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
@@ -338,11 +456,17 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     uint32_t *ev = eval + b0 * ((size_t)4 << rg.log);
     if (p <= LDE_SMEM_LOG_MAX) {
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
-      size_t smem = (size_t)4 << p;
-      if (p >= 11)
-        lde_block_kernel<1024><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, tt, rg);
-      else
-        lde_block_kernel<256><<<grid, 256, smem, st>>>(cf, ev, p, beta, n_felts, tt, rg);
+      size_t smem = ((size_t)4 << p) + (((size_t)4 << p) >> 4) + 64;  // + 4 pad words per 64
+#define FR_LDE_CASE(PP, TT) \
+  case PP: lde_block_kernel<PP, TT><<<grid, TT, smem, st>>>(cf, ev, beta, n_felts, tt, rg); break;
+      switch (p) {
+        case 0: lde_copy_kernel<<<grid, 1, 0, st>>>(cf, ev, beta, n_felts, rg); break;
+        FR_LDE_CASE(1, 32) FR_LDE_CASE(2, 32) FR_LDE_CASE(3, 32) FR_LDE_CASE(4, 32) FR_LDE_CASE(5, 32)
+        FR_LDE_CASE(6, 32) FR_LDE_CASE(7, 64) FR_LDE_CASE(8, 64) FR_LDE_CASE(9, 128) FR_LDE_CASE(10, 128)
+        FR_LDE_CASE(11, 256) FR_LDE_CASE(12, 512) FR_LDE_CASE(13, 512) FR_LDE_CASE(14, 512) FR_LDE_CASE(15, 512)
+        default: return cudaErrorInvalidValue;
+      }
+#undef FR_LDE_CASE
     } else {
       // strided passes over layers p-1 .. c, then contiguous chunks of 2^c; every tile is
       // 2^14 words (64 KiB) with rows of at least 2^5 consecutive words (128 B).  The first
