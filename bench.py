@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--blobs", type=int, default=4096, help="blobs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-passes", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -344,6 +345,15 @@ def main():
         "kernels": kernels,
     }
 
+    # free the big C3 buffers before the extra measurements
+    del d_in, d_roots, d_last
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        # BASELINE config 5: ONE 64 MiB blob at blowup 2^2 split over all ranks (subtree roots all-gathered
+        # over NCCL); strong scaling.  Every rank takes part; timed end to end (H2D of the blob included).
+        line["c5_split"] = c5_split(ctx, torch, dist, distributed, rank, world, barrier)
+    if rank == 0 and not args.no_extras:
+        line["extras"] = extras(ctx, host_np, cfg, torch)
     if rank == 0 and not args.no_passes:
         line["passes"] = standalone_passes(ctx, stream, torch, np, hbm_peak, peak_src)
         line["single_blob_latency_ms"] = single_blob_latency(ctx, host_np, cfg)
@@ -363,6 +373,69 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     return 0
+
+
+C5_ROOT = "7ab1d35e23dcb4b678524912e0fc0cdbcb6efaa34aa9f480f97f3138b3f0ee07"  # oracle, tests/golden/vectors.json
+
+
+def c5_split(ctx, torch, dist, distributed, rank, world, barrier):
+    import numpy as np
+    from frieda_b200.parallel import commit_split, is_pow2
+    if not is_pow2(world):
+        return {"skipped": "world size is not a power of two"}
+    n_bytes = 64 << 20
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n_bytes // 8 + 1, dtype=np.uint64)
+        z = (np.uint64(0x4652494544414236) + idx * np.uint64(0x9E3779B97F4A7C15)) & M
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    blob = torch.from_numpy(z.astype("<u8").view(np.uint8)).pin_memory().numpy()
+    root = commit_split(ctx, blob, 2, rank=rank, world=world)
+    ok = root.hex() == C5_ROOT
+    for _ in range(2):
+        commit_split(ctx, blob, 2, rank=rank, world=world)
+    iters = 5
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        commit_split(ctx, blob, 2, rank=rank, world=world)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    per = float(dt.item()) / iters
+    return {"workload": "C5: one 64 MiB blob, blowup 2^2, commit split into per-GPU subtrees + all-gather of roots",
+            "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "blobs_per_s": 1.0 / per,
+            "input_gb_per_s": n_bytes / per / 1e9, "n_gpus": world, "scaling": "strong",
+            "timing": "host wall clock around the synchronous call, max over ranks (H2D of the blob included)"}
+
+
+def extras(ctx, host_np, cfg, torch):
+    """Other entry points on the same synthetic blobs (rank 0): commit only (api::commit, batched) and
+    full proof generation with 64 queries per blob (BASELINE config 4)."""
+    import frieda_b200 as F
+    out = {}
+    n = min(len(host_np), 4096)
+    blobs = host_np[:n]
+    ctx.commit_batch(blobs[:256], CFG[0])
+    t0 = time.perf_counter()
+    ctx.commit_batch(blobs, CFG[0])
+    dt = time.perf_counter() - t0
+    out["commit_only_e2e"] = {"blobs": n, "blobs_per_s": n / dt, "input_gb_per_s": n * BLOB_LEN / dt / 1e9}
+    npv = min(n, 512)
+    c4 = F.PcsConfig(CFG[0], CFG[1], 64, CFG[3])
+    seeds = list(range(npv))
+    ctx.prove_batch(blobs[:64], seeds[:64], c4)
+    t0 = time.perf_counter()
+    roots, proofs = ctx.prove_batch(blobs[:npv], seeds, c4)
+    dt = time.perf_counter() - t0
+    ok = all(F.verify_proof(proofs[i], seeds[i]) for i in (0, npv // 2, npv - 1))
+    out["prove_c4_e2e"] = {"blobs": npv, "n_queries": 64, "pow_bits": CFG[3], "blobs_per_s": npv / dt,
+                           "proofs_verify": ok,
+                           "note": "commit + FRI + grind + decommit + host proof assembly, kept trees"}
+    return out
 
 
 def standalone_passes(ctx, stream, torch, np, hbm_peak, peak_src):

@@ -67,6 +67,11 @@ def main():
         ("splitmix_1MiB_b2", O.splitmix64_bytes(0x4652494544414236, 1 << 20), 2),
     ]:
         og["commit"].append({"name": name, "len": len(data), "log_blowup": blow, "root": O.commit(data, blow).hex()})
+    # BASELINE config 5 (64 MiB, blowup 2^2) and an 8 MiB sibling; ~25 s of oracle time
+    og["commit_large"] = []
+    for name, n in [("c5_splitmix_64MiB_b2", 64 << 20), ("splitmix_8MiB_b2", 8 << 20)]:
+        og["commit_large"].append({"name": name, "len": n, "log_blowup": 2, "state0": "0x4652494544414236",
+                                   "root": O.commit(O.splitmix64_bytes(0x4652494544414236, n), 2).hex()})
     og["prove"] = []
     import hashlib
     for name, data, seed, cfg in [

@@ -539,3 +539,17 @@ def test_commit_split_subroots_are_tree_nodes(ctx, torch_mod):
     for r in range(world):
         ctx.commit_split_local(data, 2, r, world, subs[r].data_ptr())
     assert subs.cpu().numpy().tobytes() == t.tree_levels[0][2].tobytes()
+
+
+def test_commit_config5_64MiB_split_and_unsplit(ctx, torch_mod, golden):
+    # BASELINE config 5 at full size: one 64 MiB blob, blowup 2^2 (poly_log 23: strided LDE passes);
+    # root from the oracle (tests/golden/make_vectors.py), unsplit and split over 8 virtual ranks
+    torch = torch_mod
+    for g in golden["oracle_generated"]["commit_large"]:
+        data = O.splitmix64_bytes(int(g["state0"], 16), g["len"])
+        assert ctx.commit(data, g["log_blowup"]).hex() == g["root"], g["name"]
+        for world in (2, 8):
+            subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+            for r in range(world):
+                ctx.commit_split_local(data, g["log_blowup"], r, world, subs[r].data_ptr())
+            assert ctx.merkle_combine(subs.data_ptr(), world).hex() == g["root"], (g["name"], world)
