@@ -14,7 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/frieda_b200.h"
@@ -52,10 +54,10 @@ struct Plan {
   uint32_t nq = 0;  // n_queries (prove)
   bool keep = false, prove = false, fri = false;
   size_t in_stride = 0;  // bytes between staged blobs
-  size_t o_in = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
+  size_t o_in = 0, o_in2 = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
   size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
   size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
-  size_t o_best = 0, o_unsolved = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
+  size_t o_best = 0, o_next = 0, o_unsolved = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
          o_evals = 0;
   size_t total = 0;
 };
@@ -81,6 +83,10 @@ size_t tree_slots(uint32_t d, bool keep, uint32_t levels_cfg) {
 struct frieda_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host-buffer entry points stage the next wave's input on copy_stream while the current wave
+  // computes: ev_copied[b] = staging buffer b holds its wave, ev_free[b] = its pack kernel has read it
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
   size_t ws_limit = 0;
@@ -101,6 +107,11 @@ struct frieda_ctx {
   size_t arena_bytes = 0;
   // small result staging
   uint8_t *d_scratch = nullptr;  // 4 KiB
+  // grow-only buffers of the proof path: gathered witnesses on the device, pinned readback on the host
+  uint8_t *d_gather = nullptr;
+  size_t d_gather_bytes = 0;
+  uint8_t *h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
   // per-kernel timing with CUDA events on the launching stream (bench.py's roofline)
   bool profiling = false;
   struct ProfRec {
@@ -252,7 +263,10 @@ void layout(Plan &pl, size_t B, bool stage_input) {
   pl.B = B;
   Bump bp;
   pl.in_stride = align_up(g.len ? g.len : 1, 16);
-  if (stage_input) pl.o_in = bp.take(B * pl.in_stride);
+  if (stage_input) {
+    pl.o_in = bp.take(B * pl.in_stride);
+    pl.o_in2 = bp.take(B * pl.in_stride);  // double buffer: the next wave is uploaded during compute
+  }
   pl.o_coef = bp.take(B * ((size_t)16 << g.p));
   const uint32_t n_cols_layers = pl.fri ? g.n_layers + 1 : 1;
   for (uint32_t l = 0; l < n_cols_layers; l++) {
@@ -275,6 +289,7 @@ void layout(Plan &pl, size_t B, bool stage_input) {
   }
   if (pl.prove) {
     pl.o_best = bp.take(B * 8);
+    pl.o_next = bp.take(B * 8);
     pl.o_unsolved = bp.take(256);
     pl.o_totals = bp.take(256);
   }
@@ -303,6 +318,8 @@ size_t pick_wave(frieda_ctx *ctx, Plan &pl, size_t n, bool stage_input, uint32_t
   if (B < 1) B = 1;
   if (B > n) B = n;
   if (B > 32768) B = 32768;
+  // host input: at least 4 waves (of >= 128 blobs) so that all but the first upload hide behind compute
+  if (stage_input && n >= 512 && B > (n + 3) / 4) B = (n + 3) / 4;
   layout(pl, B, stage_input);
   if (pl.prove) layout_prove_tail(pl, n_queries);
   return B;
@@ -377,30 +394,47 @@ int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channe
 CPoint half_initial_point(const Geom &g) { return host::point_from_index(half_odds_index(g.D - 1, 0)); }
 
 // pack + LDE of the wave's blobs (device pointer d_in, stride bytes) into cols[0]
-int lde_wave(frieda_ctx *ctx, const Plan &pl, const uint8_t *d_in, size_t stride) {
+int lde_wave(frieda_ctx *ctx, const Plan &pl, const uint8_t *d_in, size_t stride, int staged_buf = -1) {
   const Geom &g = pl.g;
   uint32_t *coef = at<uint32_t>(ctx, pl.o_coef);
   KL("pack", launch_pack(ctx->stream, d_in, g.len, stride, pl.B, g.n_felts, g.p, coef), 1);
+  if (staged_buf >= 0) CU(cudaEventRecord(ctx->ev_free[staged_buf], ctx->stream));  // staging buffer is reusable
   KL("lde", launch_lde(ctx->stream, coef, at<uint32_t>(ctx, pl.o_cols[0]), g.p, g.beta, pl.B, g.n_felts, table(ctx),
                 half_initial_point(g)),
      (g.p > 15 ? 2 : 1));
   return FRIEDA_OK;
 }
 
-int stage_in(frieda_ctx *ctx, const Plan &pl, const uint8_t *h_blobs, size_t stride, const uint8_t **d_in,
-             size_t *d_stride) {
-  uint8_t *dst = at<uint8_t>(ctx, pl.o_in);
+// Enqueues the upload of one wave (nb blobs) into staging buffer `buf` on the copy stream.
+int stage_upload(frieda_ctx *ctx, const Plan &pl, int buf, const uint8_t *h_blobs, size_t stride, size_t nb) {
+  uint8_t *dst = at<uint8_t>(ctx, buf ? pl.o_in2 : pl.o_in);
   const Geom &g = pl.g;
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));
   if (g.len) {
     if (stride == g.len && pl.in_stride == g.len) {
-      CU(cudaMemcpyAsync(dst, h_blobs, pl.B * g.len, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(dst, h_blobs, nb * g.len, cudaMemcpyHostToDevice, ctx->copy_stream));
     } else {
-      CU(cudaMemcpy2DAsync(dst, pl.in_stride, h_blobs, stride, g.len, pl.B, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpy2DAsync(dst, pl.in_stride, h_blobs, stride, g.len, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
   }
-  *d_in = dst;
+  CU(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+  return FRIEDA_OK;
+}
+// Makes the compute stream wait for staging buffer `buf`; returns its device pointer.
+int stage_acquire(frieda_ctx *ctx, const Plan &pl, int buf, const uint8_t **d_in, size_t *d_stride) {
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+  *d_in = at<uint8_t>(ctx, buf ? pl.o_in2 : pl.o_in);
   *d_stride = pl.in_stride;
   return FRIEDA_OK;
+}
+// Single-wave convenience used by the proof path.
+int stage_in(frieda_ctx *ctx, const Plan &pl, const uint8_t *h_blobs, size_t stride, const uint8_t **d_in,
+             size_t *d_stride) {
+  // the previous user of buffer 0 is ordered on ctx->stream; make the copy stream follow it
+  CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+  int rc = stage_upload(ctx, pl, 0, h_blobs, stride, pl.B);
+  if (rc) return rc;
+  return stage_acquire(ctx, pl, 0, d_in, d_stride);
 }
 
 // ---- commit ----------------------------------------------------------------------------
@@ -420,31 +454,43 @@ int commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride
   size_t B = pick_wave(ctx, pl, n, !device_io, 0);
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   ctx->have_last = false;
-  for (size_t b0 = 0; b0 < n; b0 += B) {
+  if (!device_io) {
+    // uploads run on the copy stream, one wave ahead of compute
+    CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+    if ((rc = stage_upload(ctx, pl, 0, blobs, stride, std::min(B, n)))) return rc;
+  }
+  int buf = 0;
+  for (size_t b0 = 0; b0 < n; b0 += B, buf ^= 1) {
     size_t nb = std::min(B, n - b0);
     Plan w = pl;
     w.B = nb;
     const uint8_t *d_in = blobs + b0 * stride;
     size_t d_stride = stride;
-    if (!device_io && (rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
-    if ((rc = lde_wave(ctx, w, d_in, d_stride))) return rc;
+    if (!device_io) {
+      if (b0 + B < n &&
+          (rc = stage_upload(ctx, pl, buf ^ 1, blobs + (b0 + B) * stride, stride, std::min(B, n - b0 - B))))
+        return rc;
+      if ((rc = stage_acquire(ctx, pl, buf, &d_in, &d_stride))) return rc;
+    }
+    if ((rc = lde_wave(ctx, w, d_in, d_stride, device_io ? -1 : buf))) return rc;
     uint8_t *d_roots = at<uint8_t>(ctx, w.o_roots);
     if ((rc = commit_tree(ctx, w, 0, SRC_COLS, nullptr, d_roots, 32))) return rc;
     CU(cudaMemcpyAsync(roots_out + b0 * 32, d_roots, nb * 32, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                        ctx->stream));
-    if (!device_io) CU(cudaStreamSynchronize(ctx->stream));
   }
+  if (!device_io) CU(cudaStreamSynchronize(ctx->stream));
   return FRIEDA_OK;
 }
 
 // ---- FRI commit phase for one wave; leaves all state in the arena ------------------------
-int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_stride, const uint64_t *d_seeds) {
+int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_stride, const uint64_t *d_seeds,
+             int staged_buf = -1) {
   const Geom &g = w.g;
   int rc;
-  if ((rc = lde_wave(ctx, w, d_in, d_stride))) return rc;
+  if ((rc = lde_wave(ctx, w, d_in, d_stride, staged_buf))) return rc;
   Channel *chan = at<Channel>(ctx, w.o_chan);
   KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
-  CU(cudaMemsetAsync(at<int>(ctx, w.o_err), 0, sizeof(int), ctx->stream));
   uint8_t *roots = at<uint8_t>(ctx, w.o_roots);
   const size_t roots_stride = (size_t)g.n_layers * 32;
   uint32_t layer = 0;
@@ -509,7 +555,15 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   const Geom &g = pl.g;
   const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  for (size_t b0 = 0; b0 < n; b0 += B) {
+  CU(cudaMemsetAsync(at<int>(ctx, pl.o_err), 0, sizeof(int), ctx->stream));
+  if (!device_io) {
+    // uploads run on the copy stream, one wave ahead of compute
+    CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+    if ((rc = stage_upload(ctx, pl, 0, blobs, stride, std::min(B, n)))) return rc;
+  }
+  int buf = 0;
+  for (size_t b0 = 0; b0 < n; b0 += B, buf ^= 1) {
     size_t nb = std::min(B, n - b0);
     Plan w = pl;
     w.B = nb;
@@ -517,7 +571,10 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
     size_t d_stride = stride;
     const uint64_t *d_seeds = nullptr;
     if (!device_io) {
-      if ((rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
+      if (b0 + B < n &&
+          (rc = stage_upload(ctx, pl, buf ^ 1, blobs + (b0 + B) * stride, stride, std::min(B, n - b0 - B))))
+        return rc;
+      if ((rc = stage_acquire(ctx, pl, buf, &d_in, &d_stride))) return rc;
       if (seeds) {
         CU(cudaMemcpyAsync(at<uint64_t>(ctx, w.o_seeds), seeds + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
         d_seeds = at<uint64_t>(ctx, w.o_seeds);
@@ -525,21 +582,48 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
     } else if (seeds) {
       d_seeds = seeds + b0;
     }
-    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds))) return rc;
+    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds, device_io ? -1 : buf))) return rc;
     CU(cudaMemcpyAsync(roots_out + b0 * g.n_layers * 32, at<uint8_t>(ctx, w.o_roots), nb * g.n_layers * 32, out_kind,
                        ctx->stream));
     CU(cudaMemcpyAsync(last_poly_out + (b0 << g.log_last), at<QM31>(ctx, w.o_last), (nb * sizeof(QM31)) << g.log_last,
                        out_kind, ctx->stream));
-    if (!device_io) {
-      int err_flag = 0;
-      CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, w.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
-    }
     ctx->last = w;
     ctx->have_last = true;
     ctx->last_nonces.clear();
   }
+  if (!device_io) {
+    int err_flag = 0;
+    CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, pl.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+  }
+  return FRIEDA_OK;
+}
+
+int ensure_gather(frieda_ctx *ctx, size_t bytes) {
+  if (ctx->d_gather_bytes >= bytes) return FRIEDA_OK;
+  if (ctx->d_gather) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_gather);
+    ctx->d_gather = nullptr;
+    ctx->d_gather_bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 4096;
+  CU(cudaMalloc(&ctx->d_gather, want));
+  ctx->d_gather_bytes = want;
+  return FRIEDA_OK;
+}
+int ensure_pinned(frieda_ctx *ctx, size_t bytes) {
+  if (ctx->h_pinned_bytes >= bytes) return FRIEDA_OK;
+  if (ctx->h_pinned) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr;
+    ctx->h_pinned_bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 4096;
+  CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pinned), want, cudaHostAllocDefault));
+  ctx->h_pinned_bytes = want;
   return FRIEDA_OK;
 }
 
@@ -568,10 +652,11 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   const Geom &g = pl.g;
   const uint32_t L = g.n_layers;
-  std::vector<uint8_t> h_roots, h_fri, h_hash;
+  std::vector<uint8_t> h_roots;
   std::vector<frieda_qm31> h_last, h_evals;
   std::vector<uint32_t> h_counts, h_nuniq;
   std::vector<unsigned long long> h_offsets, h_best;
+  CU(cudaMemsetAsync(at<int>(ctx, pl.o_err), 0, sizeof(int), ctx->stream));
   for (size_t b0 = 0; b0 < n; b0 += B) {
     size_t nb = std::min(B, n - b0);
     Plan w = pl;
@@ -589,18 +674,11 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     Channel *chan = at<Channel>(ctx, w.o_chan);
     unsigned long long *best = at<unsigned long long>(ctx, w.o_best);
     CU(cudaMemsetAsync(best, 0xff, nb * 8, ctx->stream));
-    uint32_t range_log = cfg->pow_bits + 2;
-    if (range_log < 14) range_log = 14;
-    if (range_log > 24) range_log = 24;
-    for (uint64_t base = 0;; base += (uint64_t)1 << range_log) {
-      KL("grind", launch_grind(ctx->stream, chan, cfg->pow_bits, base, range_log, best, nb), 1);
-      uint32_t unsolved = 0;
-      KL("count_unsolved", launch_count_unsolved(ctx->stream, best, nb, at<uint32_t>(ctx, w.o_unsolved)), 1);
-      CU(cudaMemcpyAsync(&unsolved, at<uint32_t>(ctx, w.o_unsolved), 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      if (!unsolved) break;
-      if (base >> 46) return ctx->fail_arg("proof of work search exhausted");
-    }
+    // enough CTAs to fill the GPU when the wave is small, 64 per blob otherwise
+    uint32_t ctas = 32;
+    while ((size_t)ctas * nb < 2368 && ctas < 2048) ctas <<= 1;
+    const uint64_t limit = (uint64_t)1 << (cfg->pow_bits + 12 > 62 ? 62 : cfg->pow_bits + 12);
+    KL("grind", launch_grind(ctx->stream, chan, cfg->pow_bits, limit, ctas, best, at<unsigned long long>(ctx, w.o_next), nb), 1);
     // queries + decommitment (src/proof.rs:59-66)
     uint32_t *queries = at<uint32_t>(ctx, w.o_queries);
     uint32_t *nuniq = at<uint32_t>(ctx, w.o_nuniq);
@@ -628,18 +706,17 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     CU(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     // gathered witnesses live in a separate allocation sized by the exact totals
-    uint8_t *d_gather = nullptr;
     size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
-    CU(cudaMalloc(&d_gather, align_up(fri_bytes, 256) + hash_bytes + 256));
+    const size_t fri_pad = align_up(fri_bytes, 256);
+    if ((rc = ensure_gather(ctx, fri_pad + hash_bytes + 256))) return rc;
+    if ((rc = ensure_pinned(ctx, fri_pad + hash_bytes + 256))) return rc;
+    uint8_t *d_gather = ctx->d_gather;
     dp.fri_out = reinterpret_cast<QM31 *>(d_gather);
-    dp.hash_out = d_gather + align_up(fri_bytes, 256);
+    dp.hash_out = d_gather + fri_pad;
     ctx->prof_begin("decommit_write");
     cudaError_t le = launch_decommit_write(ctx->stream, dp, nb);
     ctx->prof_end();
-    if (le != cudaSuccess) {
-      cudaFree(d_gather);
-      return ctx->fail(le, "launch_decommit_write", __LINE__);
-    }
+    if (le != cudaSuccess) return ctx->fail(le, "launch_decommit_write", __LINE__);
     ctx->launches += 2;
     h_roots.resize(nb * L * 32);
     h_last.resize(nb << g.log_last);
@@ -648,8 +725,6 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     h_offsets.resize(nb * L * 2);
     h_nuniq.resize(nb);
     h_best.resize(nb);
-    h_fri.resize(fri_bytes);
-    h_hash.resize(hash_bytes);
     int err_flag = 0;
     cudaError_t ce = cudaSuccess;
     auto cp = [&](void *dst, const void *src, size_t bytes) {
@@ -662,17 +737,22 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     cp(h_offsets.data(), dp.offsets, h_offsets.size() * 8);
     cp(h_nuniq.data(), nuniq, nb * 4);
     cp(h_best.data(), best, nb * 8);
-    cp(h_fri.data(), dp.fri_out, fri_bytes);
-    cp(h_hash.data(), dp.hash_out, hash_bytes);
+    cp(ctx->h_pinned, d_gather, fri_pad + hash_bytes);  // witnesses: one copy into pinned memory
+    const uint8_t *h_fri = ctx->h_pinned, *h_hash = ctx->h_pinned + fri_pad;
     cp(&err_flag, at<int>(ctx, w.o_err), sizeof(int));
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_gather);
     if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
     if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+    for (size_t b = 0; b < nb; b++)
+      if (h_best[b] == ~0ull) return ctx->fail_arg("proof of work search exhausted");
     // assemble Proof objects (src/proof.rs:67-76)
-    for (size_t b = 0; b < nb; b++) {
+    std::atomic<bool> oom{false};
+    auto assemble = [&](size_t b) {
       frieda_proof *pr = (frieda_proof *)std::calloc(1, sizeof(frieda_proof));
-      if (!pr) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+      if (!pr) {
+        oom = true;
+        return;
+      }
       proofs_out[b0 + b] = pr;
       pr->pcs_config = *cfg;
       pr->log_size_bound = g.p;
@@ -683,8 +763,10 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
       pr->last_layer_poly = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) << g.log_last);
       pr->n_evaluations = h_nuniq[b];
       pr->evaluations = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (h_nuniq[b] ? h_nuniq[b] : 1));
-      if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations)
-        return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+      if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations) {
+        oom = true;
+        return;
+      }
       std::memcpy(pr->last_layer_poly, &h_last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
       std::memcpy(pr->evaluations, &h_evals[b * nq], sizeof(frieda_qm31) * h_nuniq[b]);
       for (uint32_t l = 0; l < L; l++) {
@@ -697,13 +779,30 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
         lp->fri_witness = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (lp->n_fri_witness ? lp->n_fri_witness : 1));
         lp->hash_witness = (uint8_t *)std::malloc(32 * (size_t)(lp->n_hash_witness ? lp->n_hash_witness : 1));
         lp->column_witness = (uint32_t *)std::malloc(4);
-        if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness)
-          return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
-        std::memcpy(lp->fri_witness, h_fri.data() + h_offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
-        std::memcpy(lp->hash_witness, h_hash.data() + h_offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
+        if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness) {
+          oom = true;
+          return;
+        }
+        std::memcpy(lp->fri_witness, h_fri + h_offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
+        std::memcpy(lp->hash_witness, h_hash + h_offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
       }
       if (roots_out) std::memcpy(roots_out + (b0 + b) * 32, &h_roots[b * L * 32], 32);
+    };
+    {
+      // proofs are independent: assemble them on a few host threads
+      unsigned nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<size_t>(8, (nb + 31) / 32));
+      if (nt <= 1) {
+        for (size_t b = 0; b < nb; b++) assemble(b);
+      } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+          th.emplace_back([&, t]() {
+            for (size_t b = t; b < nb; b += nt) assemble(b);
+          });
+        for (auto &x : th) x.join();
+      }
     }
+    if (oom) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
     ctx->last = w;
     ctx->have_last = true;
     ctx->last_nonces.assign(h_best.begin(), h_best.end());
@@ -735,6 +834,11 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
   ctx->device = device;
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_copied[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_scratch, 4096)) != cudaSuccess) {
     g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e);
     cudaGetLastError();
@@ -762,11 +866,18 @@ void frieda_ctx_destroy(frieda_ctx *ctx) {
   cudaFree(ctx->d_itw);
   cudaFree(ctx->arena);
   cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_gather);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (auto &r : ctx->prof_recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

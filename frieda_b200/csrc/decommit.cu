@@ -12,40 +12,53 @@
 namespace frieda {
 
 // ---------------------------------------------------------------- grind
+// CpuBackend::grind returns the SMALLEST nonce whose mix has >= pow_bits trailing zeros.  Each warp
+// takes the next chunk of GR_CHUNK nonces of its blob from an atomic counter, so chunks are handed
+// out in strictly increasing order no matter when a CTA was scheduled or how fast it runs; a warp
+// stops when the chunk it was handed starts above the best nonce found so far.  Every nonce below
+// the answer is examined (the minimum is exact), little above it is, and there is no host round trip.
 constexpr int GR_THREADS = 256;
-constexpr uint32_t GR_CTA_LOG = 14;  // nonces per CTA
+constexpr uint32_t GR_CHUNK = 128;  // nonces per grab = 4 per lane
 
 __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__restrict__ chan, uint32_t pow_bits,
-                                                           uint64_t base, unsigned long long *best, uint32_t one) {
+                                                           uint64_t limit, unsigned long long *best,
+                                                           unsigned long long *next, uint32_t one) {
   const size_t blob = blockIdx.y;
-  const uint64_t start = base + ((uint64_t)blockIdx.x << GR_CTA_LOG);
-  volatile unsigned long long *vb = best + blob;
-  if (*vb < start) return;  // a smaller nonce is already known
+  const uint32_t lane = threadIdx.x & 31;
   uint32_t d[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) d[i] = chan[blob].digest[i];
-  for (uint32_t k = 0; k < (1u << GR_CTA_LOG) / GR_THREADS; k++) {
-    uint64_t nonce = start + (uint64_t)k * GR_THREADS + threadIdx.x;
-    uint32_t h[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = d[i];
-    uint32_t m[16] = {(uint32_t)nonce, (uint32_t)(nonce >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    blake2s_compress_t<0x0003u>(h, m, 0, 0, 0, 0, one);  // only the two nonce words are non-zero
-    if (digest_trailing_zeros(h) >= pow_bits) {
-      atomicMin(best + blob, (unsigned long long)nonce);
-      break;  // later nonces of this thread are larger
+  for (;;) {
+    unsigned long long start = 0, cur = 0;
+    if (lane == 0) {
+      start = atomicAdd(next + blob, (unsigned long long)GR_CHUNK);
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(best + blob));
     }
-    if ((k & 7) == 7 && *vb < start) break;
+    start = __shfl_sync(0xffffffffu, start, 0);
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    if (start > cur || start >= limit) return;
+#pragma unroll 1
+    for (uint32_t k = 0; k < GR_CHUNK / 32; k++) {
+      const uint64_t nonce = start + k * 32 + lane;
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) h[i] = d[i];
+      uint32_t m[16] = {(uint32_t)nonce, (uint32_t)(nonce >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      blake2s_compress_t<0x0003u>(h, m, 0, 0, 0, 0, one);  // only the two nonce words are non-zero
+      if (digest_trailing_zeros(h) >= pow_bits) atomicMin(best + blob, (unsigned long long)nonce);
+    }
   }
 }
 
-cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t base, uint32_t range_log,
-                         unsigned long long *best, size_t n_blobs) {
-  if (range_log < GR_CTA_LOG) range_log = GR_CTA_LOG;
-  unsigned chunks = 1u << (range_log - GR_CTA_LOG);
+cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t limit, uint32_t ctas_per_blob,
+                         unsigned long long *best, unsigned long long *next, size_t n_blobs) {
+  if (ctas_per_blob == 0) ctas_per_blob = 1;
+  cudaError_t e = cudaMemsetAsync(next, 0, n_blobs * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
-    grind_kernel<<<dim3(chunks, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, base, best + b0, 1u);
+    grind_kernel<<<dim3(ctas_per_blob, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, limit, best + b0,
+                                                                          next + b0, 1u);
   }
   return cudaGetLastError();
 }
