@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -37,6 +38,20 @@ struct Geom {
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// FRIEDA_TRACE=1: host-side stage timings of the proof path on stderr (development aid)
+struct StageTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  StageTrace() : on(std::getenv("FRIEDA_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[frieda trace] %-28s %8.1f us\n", what,
+                 std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct Bump {
   size_t off = 0;
@@ -310,18 +325,24 @@ void layout_prove_tail(Plan &pl, uint32_t n_queries) {
 }
 
 size_t pick_wave(frieda_ctx *ctx, Plan &pl, size_t n, bool stage_input, uint32_t n_queries) {
-  size_t budget = workspace_budget(ctx);
-  layout(pl, 1, stage_input);
-  if (pl.prove) layout_prove_tail(pl, n_queries);
-  size_t per_blob = pl.total + 4096;
-  size_t B = budget / per_blob;
-  if (B < 1) B = 1;
-  if (B > n) B = n;
-  if (B > 32768) B = 32768;
+  auto lay = [&](size_t B) {
+    layout(pl, B, stage_input);
+    if (pl.prove) layout_prove_tail(pl, n_queries);
+  };
+  size_t B = n > 32768 ? 32768 : n;
   // host input: at least 4 waves (of >= 128 blobs) so that all but the first upload hide behind compute
   if (stage_input && n >= 512 && B > (n + 3) / 4) B = (n + 3) / 4;
-  layout(pl, B, stage_input);
-  if (pl.prove) layout_prove_tail(pl, n_queries);
+  lay(B);
+  // fast path: the workspace we already hold fits the whole call (cudaMemGetInfo costs milliseconds)
+  if (pl.total <= ctx->arena_bytes && (!ctx->ws_limit || pl.total <= ctx->ws_limit)) return B;
+  size_t budget = workspace_budget(ctx);
+  if (pl.total <= budget) return B;
+  lay(1);
+  size_t per_blob = pl.total + 4096;
+  size_t fit = budget / per_blob;
+  if (fit < 1) fit = 1;
+  if (fit < B) B = fit;
+  lay(B);
   return B;
 }
 
@@ -639,6 +660,7 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   if (cfg->pow_bits > 40) return ctx->fail_arg("pow_bits > 40 is not supported");
   CU(cudaSetDevice(ctx->device));
   for (size_t i = 0; i < n; i++) proofs_out[i] = nullptr;
+  StageTrace tr;
   Plan pl;
   int rc = make_geom_fri(ctx, len, cfg, pl.g);
   if (rc) return rc;
@@ -649,7 +671,9 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   const uint32_t nq = (uint32_t)cfg->n_queries;
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, true, nq);
+  tr.mark("plan");
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
+  tr.mark("arena");
   const Geom &g = pl.g;
   const uint32_t L = g.n_layers;
   std::vector<uint8_t> h_roots;
@@ -670,6 +694,7 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
       d_seeds = at<uint64_t>(ctx, w.o_seeds);
     }
     if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds))) return rc;
+    tr.mark("fri launches");
     // proof of work (src/proof.rs:58): rounds of 2^22 nonces until every blob has its minimum
     Channel *chan = at<Channel>(ctx, w.o_chan);
     unsigned long long *best = at<unsigned long long>(ctx, w.o_best);
@@ -704,7 +729,9 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     KL("decommit_scan", launch_decommit_scan(ctx->stream, dp, nb, d_totals), 1);
     unsigned long long totals[2] = {0, 0};
     CU(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    tr.mark("grind+decommit launches");
     CU(cudaStreamSynchronize(ctx->stream));
+    tr.mark("sync 1 (fri+grind+count)");
     // gathered witnesses live in a separate allocation sized by the exact totals
     size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
     const size_t fri_pad = align_up(fri_bytes, 256);
@@ -740,7 +767,9 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     cp(ctx->h_pinned, d_gather, fri_pad + hash_bytes);  // witnesses: one copy into pinned memory
     const uint8_t *h_fri = ctx->h_pinned, *h_hash = ctx->h_pinned + fri_pad;
     cp(&err_flag, at<int>(ctx, w.o_err), sizeof(int));
+    tr.mark("write launch + readback enqueue");
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    tr.mark("sync 2 (write+d2h)");
     if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
     if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
     for (size_t b = 0; b < nb; b++)
@@ -802,6 +831,7 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
         for (auto &x : th) x.join();
       }
     }
+    tr.mark("assemble");
     if (oom) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
     ctx->last = w;
     ctx->have_last = true;

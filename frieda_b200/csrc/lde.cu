@@ -240,24 +240,28 @@ __device__ __forceinline__ void r16_pass(const uint32_t *__restrict__ c, uint32_
   }
 }
 
-template <int P, int THREADS>
-__global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *__restrict__ coef,
-                                                            uint32_t *__restrict__ eval, uint32_t beta,
-                                                            uint32_t n_felts, TwiddleTable tt, LdeRange rg) {
+// INPLACE: the block is a 2^P chunk of an evaluation array that already went through the layers
+// above P (large polynomials); it is read from and written back to `eval`, and `p_full` is the
+// true poly_log (for the zero-column test and the twiddle geometry D = p_full + beta).
+template <int P, int THREADS, bool INPLACE>
+__global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *coef, uint32_t *eval, uint32_t beta,
+                                                            uint32_t n_felts, TwiddleTable tt, LdeRange rg,
+                                                            uint32_t p_full) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr uint32_t p = P;
   const uint32_t hb = blockIdx.x + (uint32_t)(rg.lo >> p), col = blockIdx.y;
   const size_t blob = blockIdx.z;
   constexpr uint32_t n4 = 1u << P;
-  const uint32_t D = p + beta, K = D - 1;
-  const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
+  const uint32_t D = (INPLACE ? p_full : p) + beta, K = D - 1;
   // local window of this block inside the owned range
   const uint32_t w_lo = rg.log >= p ? 0u : (uint32_t)(rg.lo & (n4 - 1));
   const uint32_t w_n = rg.log >= p ? n4 : (1u << rg.log);
   const bool full = w_n == n4;
   // out[i], i = index inside the block, addresses the owned-range buffer (global index - rg.lo)
   uint32_t *out = eval + ((blob * 4 + col) << rg.log) + ((ptrdiff_t)((size_t)hb << p) - (ptrdiff_t)rg.lo);
-  if (n_felts <= col * n4) {  // all-zero column
+  const uint32_t *c = INPLACE ? out : coef + (blob * 4 + col) * (size_t)n4;
+  if ((uint64_t)n_felts <= ((uint64_t)col << (INPLACE ? p_full : p))) {  // all-zero column
+    if (INPLACE) return;  // the first strided pass already wrote the zeros
     for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
     return;
   }
@@ -315,111 +319,65 @@ __global__ void lde_tiny_kernel(const uint32_t *__restrict__ coef, uint32_t *__r
   for (uint32_t i = 0; i < (1u << D); i++) o[i] = v[i];
 }
 
-// Large polynomials (2^p points do not fit one CTA's shared memory): the top r layers are done
-// on strided tiles -- 2^r rows that are 2^(p-r) apart, 2^w consecutive columns each -- so that
-// every global access is a contiguous 2^w-word segment; the remaining layers run per
-// contiguous chunk.  FIRST reads the replicated coefficients (index mod 2^p), later passes work
-// in place on the evaluations.
-template <int THREADS, bool FIRST>
-__global__ void __launch_bounds__(THREADS) lde_strided_kernel(const uint32_t *__restrict__ coef,
-                                                              uint32_t *__restrict__ eval, uint32_t p, uint32_t beta,
-                                                              uint32_t n_felts, uint32_t top, uint32_t r, uint32_t w,
+// Large polynomials (2^p points do not fit one CTA's shared memory): the layers above the final
+// 2^c chunks are done 4 at a time by a register-only radix-16 pass.  A thread owns one column
+// position and the 16 rows that are 2^(top-4) apart; a warp reads/writes 32 consecutive words of
+// each row (128 B), so every access is coalesced and nothing goes through shared memory.  FIRST
+// reads the replicated coefficients (index mod 2^p) and may compute rows outside the owned range
+// (only in-range rows are stored); later passes work in place inside the owned range.
+template <bool FIRST>
+__global__ void __launch_bounds__(256) lde_strided_r16_kernel(const uint32_t *__restrict__ coef, uint32_t *eval,
+                                                              uint32_t p, uint32_t beta, uint32_t n_felts, uint32_t top,
                                                               TwiddleTable tt, LdeRange rg) {
-  // handles layers top-1 .. top-r of every 2^top-point sub-FFT; rows are 2^(top-r) apart
-  extern __shared__ uint32_t sm[];
   const uint32_t D = p + beta, K = D - 1;
   const uint32_t col = blockIdx.y;
   const size_t blob = blockIdx.z;
-  const uint32_t row_stride_log = top - r;                 // distance between rows (log)
-  const uint32_t tiles_per_sub = 1u << (row_stride_log - w);  // tiles inside one sub-FFT
-  // which 2^top-point sub-FFT (global index); only those touching the owned range are launched
-  const uint32_t sub = blockIdx.x / tiles_per_sub + (uint32_t)(rg.lo >> top);
-  const uint32_t tile = blockIdx.x % tiles_per_sub;
-  const size_t base = ((size_t)sub << top) + ((size_t)tile << w);
-  const uint32_t n4 = 1u << p;
-  // evaluations are stored for the owned range only: local address = global index - rg.lo
-  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) - rg.lo;
+  const uint32_t rs = top - 4;  // log2 of the row stride
+  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) - rg.lo;  // local address = global index - rg.lo
   const size_t rg_hi = rg.lo + ((size_t)1 << rg.log);
-  const uint32_t rows = 1u << r, cols = 1u << w;
-  uint32_t first = col * n4;
-  uint32_t nz = n_felts > first ? (n_felts - first < n4 ? n_felts - first : n4) : 0u;
+  const bool zero_col = (uint64_t)n_felts <= ((uint64_t)col << p);
+  if (zero_col && !FIRST) return;
+  // one thread per (sub-FFT, column position); sub-FFTs touching the owned range only
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t sub = (t >> rs) + (rg.lo >> top);
+  const size_t pos = t & (((size_t)1 << rs) - 1);
+  const size_t base = (sub << top) + pos;
+  uint32_t v[16];
   if (FIRST) {
-    const uint32_t *c = coef + (blob * 4 + col) * (size_t)n4;
-    for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
-      uint32_t row = e >> w, cc = e & (cols - 1);
-      size_t idx = base + ((size_t)row << row_stride_log) + cc;
-      uint32_t j = (uint32_t)(idx & (n4 - 1));
-      sm[e] = j < nz ? c[j] : 0u;
+    if (zero_col) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        size_t idx = base + ((size_t)j << rs);
+        if (idx >= rg.lo && idx < rg_hi) ev[idx] = 0u;
+      }
+      return;
     }
+    const uint32_t *c = coef + ((blob * 4 + col) << p);
+    const size_t mask = ((size_t)1 << p) - 1;
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = __ldg(c + ((base + ((size_t)j << rs)) & mask));
   } else {
-    for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
-      uint32_t row = e >> w, cc = e & (cols - 1);
-      sm[e] = ev[base + ((size_t)row << row_stride_log) + cc];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = ev[base + ((size_t)j << rs)];
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const uint32_t i = top - 1 - s;
+    // twiddle index of element j: (global index) >> (i + 1) = (sub << s) | (j >> (4 - s))
+    const uint32_t *tw = tt.blk(1u << (K - i)) + (sub << s);
+    const int half = 8 >> s;
+#pragma unroll
+    for (int q = 0; q < (1 << s); q++) {
+      uint32_t tv = __ldg(tw + q);
+      uint32_t t2 = tv + tv;
+#pragma unroll
+      for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2);
     }
   }
-  __syncthreads();
-  const uint32_t half = (rows * cols) >> 1;
-  for (int li = (int)r - 1; li >= 0; li--) {
-    // local row bit li <-> global layer i = row_stride_log + li
-    const uint32_t i = row_stride_log + li;
-    const uint32_t *tw = tt.blk(1u << (K - i));
-    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-      uint32_t cc = bf & (cols - 1), rb = bf >> w;  // rb indexes row pairs
-      uint32_t lo = rb & ((1u << li) - 1), hi = rb >> li;
-      uint32_t ra = (hi << (li + 1)) | lo, rbb = ra + (1u << li);
-      size_t ga = base + ((size_t)ra << row_stride_log) + cc;  // global index of element a
-      uint32_t t = __ldg(tw + (ga >> (i + 1)));
-      uint32_t a = (ra << w) | cc, b = (rbb << w) | cc;
-      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
-      sm[a] = m31_add(va, tmp);
-      sm[b] = m31_sub(va, tmp);
-    }
-    __syncthreads();
-  }
-  for (uint32_t e = threadIdx.x; e < rows * cols; e += THREADS) {
-    uint32_t row = e >> w, cc = e & (cols - 1);
-    size_t idx = base + ((size_t)row << row_stride_log) + cc;
-    if (idx >= rg.lo && idx < rg_hi) ev[idx] = sm[e];
-  }
-}
-
-// Contiguous chunk pass, in place on the evaluations: layers c-1 .. 0 of every 2^c chunk.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) lde_chunk_kernel(uint32_t *__restrict__ eval, uint32_t D, uint32_t c,
-                                                            TwiddleTable tt, LdeRange rg) {
-  extern __shared__ uint32_t sm[];
-  const uint32_t K = D - 1;
-  const uint32_t col = blockIdx.y;
-  const size_t blob = blockIdx.z;
-  const size_t chunk = blockIdx.x + (rg.lo >> c);  // global chunk index
-  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) + ((size_t)blockIdx.x << c);
-  const uint32_t n = 1u << c;
-  for (uint32_t i = threadIdx.x; i < n; i += THREADS) sm[i] = ev[i];
-  __syncthreads();
-  const uint32_t half = n >> 1;
-  for (int i = (int)c - 1; i >= 1; i--) {
-    const uint32_t *tw = tt.blk(1u << (K - i)) + (chunk << (c - i - 1));
-    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-      uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
-      uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
-      uint32_t t = __ldg(tw + hi);
-      uint32_t va = sm[a], tmp = m31_mul(sm[b], t);
-      sm[a] = m31_add(va, tmp);
-      sm[b] = m31_sub(va, tmp);
-    }
-    __syncthreads();
-  }
-  const uint32_t *tw = tt.blk(1u << (K - 1));
-  for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-    size_t h = (chunk << (c - 1)) | bf;
-    size_t q = h >> 2;
-    uint32_t e = (uint32_t)(h & 3);
-    uint32_t x = __ldg(tw + 2 * q), y = __ldg(tw + 2 * q + 1);
-    uint32_t t = e == 0 ? y : e == 1 ? m31_neg(y) : e == 2 ? m31_neg(x) : x;
-    uint2 v = reinterpret_cast<const uint2 *>(sm)[bf];
-    uint32_t tmp = m31_mul(v.y, t);
-    uint2 rr = {m31_add(v.x, tmp), m31_sub(v.x, tmp)};
-    reinterpret_cast<uint2 *>(ev)[bf] = rr;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    size_t idx = base + ((size_t)j << rs);
+    if (!FIRST || (idx >= rg.lo && idx < rg_hi)) ev[idx] = v[j];
   }
 }
 
@@ -439,15 +397,16 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     return cudaGetLastError();
   }
   static bool attr_set = false;
+  const int big = (4 << LDE_SMEM_LOG_MAX) + (4 << LDE_SMEM_LOG_MAX) / 16 + 64;
   if (!attr_set) {
-    const int big = (4 << LDE_SMEM_LOG_MAX) + (4 << LDE_SMEM_LOG_MAX) / 16 + 64;
-    cudaFuncSetAttribute(lde_block_kernel<12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<13, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<14, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_strided_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
-    cudaFuncSetAttribute(lde_strided_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16);
-    cudaFuncSetAttribute(lde_chunk_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << LDE_SMEM_LOG_MAX);
+    cudaFuncSetAttribute(lde_block_kernel<12, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<13, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<14, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<12, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<13, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<14, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_set = true;
   }
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
@@ -458,7 +417,7 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
       size_t smem = ((size_t)4 << p) + (((size_t)4 << p) >> 4) + 64;  // + 4 pad words per 64
 #define FR_LDE_CASE(PP, TT) \
-  case PP: lde_block_kernel<PP, TT><<<grid, TT, smem, st>>>(cf, ev, beta, n_felts, tt, rg); break;
+  case PP: lde_block_kernel<PP, TT, false><<<grid, TT, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
       switch (p) {
         case 0: lde_copy_kernel<<<grid, 1, 0, st>>>(cf, ev, beta, n_felts, rg); break;
         FR_LDE_CASE(1, 32) FR_LDE_CASE(2, 32) FR_LDE_CASE(3, 32) FR_LDE_CASE(4, 32) FR_LDE_CASE(5, 32)
@@ -468,37 +427,30 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       }
 #undef FR_LDE_CASE
     } else {
-      // strided passes over layers p-1 .. c, then contiguous chunks of 2^c; every tile is
-      // 2^14 words (64 KiB) with rows of at least 2^5 consecutive words (128 B).  The first
-      // pass reads the coefficients, so it may compute more rows than the owned range keeps;
-      // it is made deep enough that every later pass stays inside the owned range.
-      const uint32_t c = 14;
-      if (rg.log < c) return cudaErrorInvalidValue;
-      const uint32_t n_passes = (p - c + 8) / 9;
+      // m register-only radix-16 passes over layers p-1 .. c, then 2^c chunks in shared memory;
+      // c = p - 4m lies in 12..15.  After the first pass everything stays inside the owned range.
+      const uint32_t m = (p - LDE_SMEM_LOG_MAX + 3) / 4;
+      const uint32_t c = p - 4 * m;
+      if (rg.log < c || (rg.log < p && p - rg.log > 4)) return cudaErrorInvalidValue;
       uint32_t top = p;
-      bool firstpass = true;
-      for (uint32_t pass = 0; pass < n_passes; pass++) {
-        uint32_t left = n_passes - pass;
-        uint32_t r = (top - c + left - 1) / left;
-        if (firstpass && rg.log < top && top - rg.log > r) r = top - rg.log;
-        if (r > 9) return cudaErrorInvalidValue;
-        uint32_t w = 14 - r;
-        // sub-FFTs of 2^top points touching the range
-        uint32_t subs = rg.log >= top ? 1u << (rg.log - top) : 1u;
-        uint32_t tiles = subs << (top - r - w);
-        dim3 grid(tiles, 4, (unsigned)nb);
-        size_t smem = (size_t)4 << (r + w);
-        if (firstpass)
-          lde_strided_kernel<1024, true><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt, rg);
+      for (uint32_t pass = 0; pass < m; pass++, top -= 4) {
+        // threads = (sub-FFTs touching the range) x 2^(top-4) column positions
+        size_t subs = rg.log >= top ? (size_t)1 << (rg.log - top) : 1;
+        size_t threads = subs << (top - 4);
+        dim3 grid((unsigned)(threads / 256), 4, (unsigned)nb);
+        if (pass == 0)
+          lde_strided_r16_kernel<true><<<grid, 256, 0, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
         else
-          lde_strided_kernel<1024, false><<<grid, 1024, smem, st>>>(cf, ev, p, beta, n_felts, top, r, w, tt, rg);
-        firstpass = false;
-        top -= r;
-        if (top == c) break;
+          lde_strided_r16_kernel<false><<<grid, 256, 0, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
       }
-      if (top != c) return cudaErrorInvalidValue;
       dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
-      lde_chunk_kernel<1024><<<grid, 1024, (size_t)4 << c, st>>>(ev, D, c, tt, rg);
+      size_t smem = ((size_t)4 << c) + (((size_t)4 << c) >> 4) + 64;
+      switch (c) {
+        case 12: lde_block_kernel<12, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        case 13: lde_block_kernel<13, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        case 14: lde_block_kernel<14, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        default: lde_block_kernel<15, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+      }
     }
   }
   return cudaGetLastError();
