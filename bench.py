@@ -308,29 +308,38 @@ def main():
     N = 1 << 18
     dominant = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
     dom_name, (dom_launches, dom_ms) = dominant
-    # algorithmic bytes per launch: bottom pass over layer 0 reads the 4 evaluation
-    # columns (16 B/leaf) and writes one 32-B subtree root per 1024 leaves, per blob
-    alg_bytes = {"merkle_bottom_cols": n * (16 * N + 32 * (N >> 10)),
-                 "fold_circle+merkle_bottom": n * (16 * N + 8 * N + 32 * (N >> 11)),
+    # algorithmic bytes per launch: the depth-3 bottom pass over layer 0 reads the 4
+    # evaluation columns (16 B per leaf) and writes one 32-B node per 8 leaves, per blob
+    alg_bytes = {"merkle_bottom_cols": n * (16 * N + 32 * (N >> 3)),
+                 "fold_circle+merkle_bottom": n * (16 * N + 8 * N + 32 * (N >> 4)),
                  }.get(dom_name)
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_metrics.txt: 1.2417 GB read + 0.2957 GB written at 296 blobs per launch), per blob
+    ncu_traffic_per_blob = {"merkle_bottom_cols": (1.241675e9 + 0.295743744e9) / 296}.get(dom_name)
     roofline = None
     if dom_name and dom_launches and alg_bytes:
         per_launch_s = dom_ms / 1e3 / dom_launches
         achieved = alg_bytes / per_launch_s / 1e9
         roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak,
+                    "traffic": ncu_traffic_per_blob * n if ncu_traffic_per_blob else None,
+                    "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                     "avg_launch_ms": dom_ms / dom_launches, "share_of_step": dom_ms / ms_dev,
-                    "note": "INT32-issue bound (BLAKE2s), not HBM bound: see int_roofline and DESIGN.md"}
+                    "note": "this kernel is INT ALU-pipe bound (BLAKE2s), not HBM bound: see int_roofline; the HBM "
+                            "roof applies to the LDE / fold passes under `passes`. traffic = ncu DRAM bytes per blob "
+                            "at 296 blobs per launch scaled to this launch's blob count"}
     kernels = {k: {"launches": v[0], "total_ms": round(v[1], 3), "share": round(v[1] / ms_dev, 4)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])} if prof else {}
-    # integer roofline: compressions per blob (SURVEY 8d, C2 commit+FRI = 1,048,498) x 976 SASS-level
-    # integer instructions, against 148 SMs x 4 SMSPs x 32 lanes x clock issue slots
+    # integer roofline: compressions per blob (SURVEY 8d, C2 commit+FRI = 1,048,498).  Each needs 648
+    # xor/rotate instructions that only the ALU pipe executes, at 0.5 warp-instr/clk/SMSP (measured,
+    # profiles/r01_pipe_rates_b200.txt): peak = 592 SMSPs x 32 lanes x clk / (648 x 2)
     compress_per_blob = 1048498
     hashes_per_s = value / world * compress_per_blob
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6
-    int_roofline = {"hashes_per_s_per_gpu": hashes_per_s, "instr_per_hash": 976,
-                    "issue_slot_frac": hashes_per_s * 976 / issue_peak, "sm_mhz_used": sm_mhz}
+    int_peak = 148 * 4 * 32 * sm_mhz * 1e6 / (648 * 2)
+    int_roofline = {"bound": "int_alu_pipe", "achieved": hashes_per_s, "peak": int_peak, "unit": "compressions/s",
+                    "frac": hashes_per_s / int_peak, "alu_instr_per_compression_floor": 648, "sm_mhz_used": sm_mhz,
+                    "note": "whole step incl. LDE/fold time; hash kernels alone run at ~0.87 of this roof"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -90,6 +90,7 @@ EXPORTS = [
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
     "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_commit_split_local",
+    "frieda_commit_split_local_device",
     "frieda_merkle_combine", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
@@ -136,6 +137,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_proof_serialize": (sz, [pp, vp, sz]),
         "frieda_proof_deserialize": (C.c_int, [C.c_char_p, sz, C.POINTER(pp)]),
         "frieda_commit_split_local": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+        "frieda_commit_split_local_device": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_merkle_combine": (C.c_int, [vp, vp, C.c_uint32, u8p]),
         "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
         "frieda_pass_lde": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp]),
@@ -392,6 +394,11 @@ class Context:
         a = _as_u8(data)
         self._check(self._L.frieda_commit_split_local(self._h, a.ctypes.data, a.size, log_blowup_factor, rank, world,
                                                       subroot_dev_ptr))
+
+    def commit_split_local_device(self, data_dev_ptr: int, length: int, log_blowup_factor: int, rank: int, world: int,
+                                  subroot_dev_ptr: int):
+        self._check(self._L.frieda_commit_split_local_device(self._h, data_dev_ptr, length, log_blowup_factor, rank,
+                                                             world, subroot_dev_ptr))
 
     def merkle_combine(self, subroots_dev_ptr: int, world: int) -> bytes:
         out = (C.c_uint8 * 32)()

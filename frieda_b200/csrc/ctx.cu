@@ -1027,8 +1027,8 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
 // strides first, so that range is computable from the coefficient vector alone (launch_lde with an
 // owned range): no exchange of evaluations.  Only the 32-byte subtree roots travel (NCCL
 // all-gather in the host layer), then frieda_merkle_combine hashes the top g levels.
-int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
-                              uint32_t world, uint8_t *d_subroot_out) {
+static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
+                                   uint32_t rank, uint32_t world, uint8_t *d_subroot_out, bool device_input) {
   if (!ctx) return FRIEDA_ERR_ARG;
   if ((!data && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || rank >= world) return ctx->fail_arg("world must be a power of two > rank");
@@ -1054,8 +1054,12 @@ int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, 
   size_t o_tree = bp.take(slots * 32);
   if ((rc = ensure_arena(ctx, bp.off))) return rc;
   ctx->have_last = false;
-  uint8_t *d_in = at<uint8_t>(ctx, o_in);
-  if (len) CU(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, ctx->stream));
+  const uint8_t *d_in = data;
+  if (!device_input) {
+    uint8_t *stage = at<uint8_t>(ctx, o_in);
+    if (len) CU(cudaMemcpyAsync(stage, data, len, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = stage;
+  }
   uint32_t *coef = at<uint32_t>(ctx, o_coef);
   uint32_t *eval = at<uint32_t>(ctx, o_eval);
   KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
@@ -1072,6 +1076,15 @@ int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, 
   CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return FRIEDA_OK;
+}
+
+int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
+                              uint32_t world, uint8_t *d_subroot_out) {
+  return commit_split_local_impl(ctx, data, len, log_blowup, rank, world, d_subroot_out, false);
+}
+int frieda_commit_split_local_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t log_blowup,
+                                     uint32_t rank, uint32_t world, uint8_t *d_subroot_out) {
+  return commit_split_local_impl(ctx, d_data, len, log_blowup, rank, world, d_subroot_out, true);
 }
 
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]) {

@@ -39,10 +39,23 @@ def all_gather_roots(subroot, group=None):
     return out
 
 
+def slice_bounds(n_bytes: int, rank: int, world: int) -> Tuple[int, int]:
+    """Byte range of the input that `rank` uploads in the sharded-upload mode (16-byte aligned cuts)."""
+    per = -(-n_bytes // world)
+    per = (per + 15) // 16 * 16
+    lo = min(n_bytes, rank * per)
+    return lo, min(n_bytes, lo + per)
+
+
 def commit_split(ctx, data, log_blowup_factor: int, group=None, rank: Optional[int] = None,
-                 world: Optional[int] = None) -> bytes:
+                 world: Optional[int] = None, sharded_upload: Optional[bool] = None) -> bytes:
     """commit() of ONE blob with the evaluation domain split across the ranks of `group`.
-    Every rank passes the same `data`; every rank returns the same 32-byte root."""
+    Every rank passes the same `data`; every rank returns the same 32-byte root.
+
+    sharded_upload (default: on when world > 1): each rank copies only its 1/world slice of the input
+    to its GPU over its own PCIe link and the slices are all-gathered over NVLink (NCCL), instead of
+    every rank uploading the whole blob."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     distributed = dist.is_available() and dist.is_initialized()
@@ -54,7 +67,25 @@ def commit_split(ctx, data, log_blowup_factor: int, group=None, rank: Optional[i
         raise ValueError("commit_split needs a power-of-two number of ranks")
     dev = torch.device("cuda", ctx.device)
     sub = torch.zeros(32, dtype=torch.uint8, device=dev)
-    ctx.commit_split_local(data, log_blowup_factor, rank, world, sub.data_ptr())
+    if sharded_upload is None:
+        sharded_upload = world > 1 and distributed
+    if sharded_upload and world > 1:
+        host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        host = host.reshape(-1).view(np.uint8)
+        n_bytes = host.size
+        per = slice_bounds(n_bytes, 0, world)[1]
+        full = torch.empty(per * world, dtype=torch.uint8, device=dev)
+        lo, hi = slice_bounds(n_bytes, rank, world)
+        mine = full[rank * per: (rank + 1) * per]
+        if hi > lo:
+            mine[: hi - lo].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
+        if hi - lo < per:
+            mine[hi - lo:].zero_()
+        dist.all_gather_into_tensor(full, mine.clone(), group=group)
+        torch.cuda.current_stream(dev).synchronize()
+        ctx.commit_split_local_device(full.data_ptr(), n_bytes, log_blowup_factor, rank, world, sub.data_ptr())
+    else:
+        ctx.commit_split_local(data, log_blowup_factor, rank, world, sub.data_ptr())
     if world == 1:
         gathered = sub.reshape(1, 32)
     else:

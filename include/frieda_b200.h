@@ -150,6 +150,10 @@ int frieda_proof_deserialize(const uint8_t *bytes, size_t len, frieda_proof **pr
  * Merkle subtree over it.  d_subroot_out: 32 bytes of device memory (the all-gather input). */
 int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
                               uint32_t rank, uint32_t world, uint8_t *d_subroot_out);
+/* Same with the whole blob already resident in device memory (e.g. each rank uploaded 1/world of it
+ * over its own PCIe link and the slices were all-gathered over NVLink). */
+int frieda_commit_split_local_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t log_blowup,
+                                     uint32_t rank, uint32_t world, uint8_t *d_subroot_out);
 /* Hashes the top log2(world) Merkle levels over the gathered subtree roots
  * (d_subroots = world * 32 bytes of device memory, rank order) into root_out (host). */
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]);

@@ -75,3 +75,15 @@ def test_subtree_root_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_slice_bounds_cover_the_blob():
+    for n in (0, 1, 15, 16, 17, 1000, 64 << 20, (64 << 20) + 5):
+        for world in (1, 2, 4, 8):
+            spans = [parallel.slice_bounds(n, r, world) for r in range(world)]
+            per = spans[0][1] - spans[0][0] if n else 0
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, _) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(lo % 16 == 0 or lo == n for lo, _ in spans)
+            assert all(lo == min(n, r * per) for r, (lo, _) in enumerate(spans)) or n == 0
