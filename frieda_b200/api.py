@@ -89,7 +89,7 @@ EXPORTS = [
     "frieda_ctx_launch_count", "frieda_ctx_stream", "frieda_ctx_set_profiling", "frieda_ctx_profile_read", "frieda_commit", "frieda_commit_batch",
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
     "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_proof_free",
-    "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_commit_split_local",
+    "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device",
     "frieda_merkle_combine", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
@@ -136,6 +136,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_proof_clone": (pp, [pp]),
         "frieda_proof_serialize": (sz, [pp, vp, sz]),
         "frieda_proof_deserialize": (C.c_int, [C.c_char_p, sz, C.POINTER(pp)]),
+        "frieda_proof_serialize_bincode": (sz, [pp, vp, sz]),
         "frieda_commit_split_local": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_commit_split_local_device": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_merkle_combine": (C.c_int, [vp, vp, C.c_uint32, u8p]),
@@ -194,6 +195,14 @@ class Proof:
         n = L.frieda_proof_serialize(self._ptr, None, 0)
         buf = (C.c_uint8 * n)()
         L.frieda_proof_serialize(self._ptr, buf, n)
+        return bytes(buf)
+
+    def serialize_bincode(self) -> bytes:
+        """bincode-1.x layout of the reference's serde `Proof` (unvalidated against Rust)."""
+        L = load_library()
+        n = L.frieda_proof_serialize_bincode(self._ptr, None, 0)
+        buf = (C.c_uint8 * n)()
+        L.frieda_proof_serialize_bincode(self._ptr, buf, n)
         return bytes(buf)
 
     @staticmethod

@@ -161,6 +161,46 @@ size_t frieda_proof_serialize(const frieda_proof *p, uint8_t *out, size_t cap) {
   return w.n;
 }
 
+// bincode 1.x default configuration (little-endian, fixed-width integers, u64 sequence lengths) of the
+// reference's `#[derive(Serialize)] struct Proof` (src/proof.rs:19-26) with stwo's field order:
+//   Proof { proof: FriProof { first_layer, inner_layers: Vec<FriLayerProof>, last_layer_poly: LinePoly { coeffs,
+//   log_size } }, proof_of_work: u64, pcs_config: PcsConfig { pow_bits, fri_config: FriConfig { log_blowup_factor,
+//   log_last_layer_degree_bound, n_queries: usize } }, log_size_bound: u32, evaluations: Vec<QM31> }
+//   FriLayerProof { fri_witness: Vec<QM31>, decommitment: MerkleDecommitment { hash_witness: Vec<[u8; 32]>,
+//   column_witness: Vec<M31> }, commitment: [u8; 32] }
+// UNVALIDATED against the Rust crate (no Rust toolchain in this image).
+size_t frieda_proof_serialize_bincode(const frieda_proof *p, uint8_t *out, size_t cap) {
+  Writer w{out, cap, 0};
+  auto seq_qm31 = [&](const frieda_qm31 *q, uint32_t k) {
+    w.u64(k);
+    for (uint32_t i = 0; i < k; i++)
+      for (int j = 0; j < 4; j++) w.u32(q[i].v[j]);
+  };
+  auto layer = [&](const frieda_layer_proof *l) {
+    seq_qm31(l->fri_witness, l->n_fri_witness);
+    w.u64(l->n_hash_witness);
+    w.bytes(l->hash_witness, 32 * (size_t)l->n_hash_witness);
+    w.u64(l->n_column_witness);
+    for (uint32_t i = 0; i < l->n_column_witness; i++) w.u32(l->column_witness[i]);
+    w.bytes(l->commitment, 32);
+  };
+  layer(&p->first_layer);
+  w.u64(p->n_inner_layers);
+  for (uint32_t i = 0; i < p->n_inner_layers; i++) layer(&p->inner_layers[i]);
+  seq_qm31(p->last_layer_poly, p->n_last_layer_poly);
+  uint32_t log_size = 0;
+  while ((1u << log_size) < p->n_last_layer_poly) log_size++;
+  w.u32(log_size);
+  w.u64(p->proof_of_work);
+  w.u32(p->pcs_config.pow_bits);
+  w.u32(p->pcs_config.log_blowup_factor);
+  w.u32(p->pcs_config.log_last_layer_degree_bound);
+  w.u64(p->pcs_config.n_queries);
+  w.u32(p->log_size_bound);
+  seq_qm31(p->evaluations, p->n_evaluations);
+  return w.n;
+}
+
 int frieda_proof_deserialize(const uint8_t *bytes, size_t len, frieda_proof **proof_out) {
   if (!bytes || !proof_out) return FRIEDA_ERR_ARG;
   Reader r{bytes, len, 0, true};

@@ -143,6 +143,9 @@ frieda_proof *frieda_proof_clone(const frieda_proof *proof);
  * Returns the byte count; writes only if cap is large enough. */
 size_t frieda_proof_serialize(const frieda_proof *proof, uint8_t *out, size_t cap);
 int frieda_proof_deserialize(const uint8_t *bytes, size_t len, frieda_proof **proof_out);
+/* bincode-1.x layout of the reference's serde-derived `Proof` (src/proof.rs:19-26), for interchange with
+ * the Rust crate.  Unvalidated: no Rust toolchain exists in the build image. */
+size_t frieda_proof_serialize_bincode(const frieda_proof *proof, uint8_t *out, size_t cap);
 
 /* ---- one oversized blob split across GPUs (BASELINE config 5) -------------------------
  * Rank `rank` of `world` (a power of two) computes the LDE of its contiguous bit-reversed

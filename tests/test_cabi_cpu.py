@@ -141,3 +141,19 @@ def test_host_verifier_on_other_shapes(case, golden):
     p = F.Proof.deserialize(pr.serialize())
     assert F.verify_proof(p, g["seed"])
     assert not F.verify_proof(p, (g["seed"] or 0) + 1)
+
+
+def test_bincode_layout_shape(oracle_proof):
+    # structure check of the serde/bincode-1.x encoding (it cannot be validated against Rust here):
+    # total length = sum of the field encodings, first u64 = first layer's fri_witness count
+    import struct
+    p = F.Proof.deserialize(oracle_proof.serialize())
+    b = p.serialize_bincode()
+    c = p.c
+    def layer_len(l):
+        return 8 + 16 * l.n_fri_witness + 8 + 32 * l.n_hash_witness + 8 + 4 * l.n_column_witness + 32
+    want = layer_len(c.first_layer) + 8 + sum(layer_len(c.inner_layers[i]) for i in range(c.n_inner_layers))
+    want += 8 + 16 * c.n_last_layer_poly + 4 + 8 + 4 + 4 + 4 + 8 + 4 + 8 + 16 * c.n_evaluations
+    assert len(b) == want
+    assert struct.unpack_from("<Q", b, 0)[0] == c.first_layer.n_fri_witness
+    assert struct.unpack_from("<Q", b, len(b) - 8 - 16 * c.n_evaluations)[0] == c.n_evaluations
