@@ -445,6 +445,19 @@ def extras(ctx, host_np, cfg, torch):
     ctx.set_profiling(False)
     prof = ctx.profile_read(reset=True)
     ok = all(F.verify_proof(proofs[i], seeds[i]) for i in (0, npv // 2, npv - 1))
+    # GPU batch verification of those proofs next to the host verifier
+    many = (proofs * ((4096 + npv - 1) // npv))[:4096]
+    many_seeds = (seeds * ((4096 + npv - 1) // npv))[:4096]
+    ctx.verify_batch(many[:256], many_seeds[:256])
+    t0 = time.perf_counter()
+    res = ctx.verify_batch(many, many_seeds)
+    dtv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host_ok = all(F.verify_proof(proofs[i], seeds[i]) for i in range(32))
+    dth = (time.perf_counter() - t0) / 32
+    out["verify_batch"] = {"proofs": len(many), "all_valid": all(r == 1 for r in res) and host_ok,
+                           "proofs_per_s": len(many) / dtv, "host_verifier_proofs_per_s_1_thread": 1.0 / dth,
+                           "note": "wall clock incl. host serialisation + H2D of the proofs (132 KB each)"}
     out["prove_c4_e2e"] = {"blobs": npv, "n_queries": 64, "pow_bits": CFG[3], "blobs_per_s": npv / dt,
                            "proofs_verify": ok, "wall_ms": dt * 1e3,
                            "kernel_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},

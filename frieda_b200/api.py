@@ -88,7 +88,8 @@ EXPORTS = [
     "frieda_ctx_create", "frieda_ctx_destroy", "frieda_last_error", "frieda_ctx_set_workspace_limit",
     "frieda_ctx_launch_count", "frieda_ctx_stream", "frieda_ctx_set_profiling", "frieda_ctx_profile_read", "frieda_commit", "frieda_commit_batch",
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
-    "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_proof_free",
+    "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_verify_batch",
+    "frieda_verify_core_host", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device",
     "frieda_merkle_combine", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
@@ -132,6 +133,8 @@ def load_library(build_if_missing: bool = True):
         "frieda_prove": (C.c_int, [vp, vp, sz, u64p, cfgp, u8p, C.POINTER(pp)]),
         "frieda_prove_batch": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, C.POINTER(pp)]),
         "frieda_verify": (C.c_int, [pp, u64p]),
+        "frieda_verify_batch": (C.c_int, [vp, C.POINTER(pp), sz, vp, C.POINTER(C.c_int)]),
+        "frieda_verify_core_host": (C.c_int, [pp, u64p]),
         "frieda_proof_free": (None, [pp]),
         "frieda_proof_clone": (pp, [pp]),
         "frieda_proof_serialize": (sz, [pp, vp, sz]),
@@ -398,6 +401,18 @@ class Context:
                                                roots.ctypes.data, arr))
         return roots, [Proof(arr[i]) for i in range(n)]
 
+    def verify_batch(self, proofs: Sequence["Proof"], seeds: Optional[Sequence[int]]) -> List[int]:
+        """GPU batch verification: 1 valid / 0 invalid / -1 where the reference panics, per proof."""
+        n = len(proofs)
+        arr = (C.POINTER(ProofStruct) * n)(*[p.ptr for p in proofs])
+        res = (C.c_int * n)()
+        sd = None
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+            assert sd.shape == (n,)
+        self._check(self._L.frieda_verify_batch(self._h, arr, n, sd.ctypes.data if sd is not None else None, res))
+        return [int(x) for x in res]
+
     # -- split blob ----------------------------------------------------------------
     def commit_split_local(self, data, log_blowup_factor: int, rank: int, world: int, subroot_dev_ptr: int):
         a = _as_u8(data)
@@ -452,6 +467,13 @@ def verify_proof(proof: Proof, seed: Optional[int]) -> bool:
     if rc < 0:
         raise FriedaError(rc, "verify failed")
     return bool(rc)
+
+
+def verify_core_host(proof: Proof, seed: Optional[int]) -> int:
+    """The GPU batch verifier's core executed on the CPU for one proof: 1 / 0 / -1 (reference panics)."""
+    L = load_library()
+    sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+    return int(L.frieda_verify_core_host(proof.ptr, sp))
 
 
 # ---- module-level functions with the reference's names (default context on device 0) ----------

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/frieda_b200.h"
+#include "ctx_internal.h"
 #include "host_math.hpp"
 #include "kernels.cuh"
 
@@ -913,6 +914,13 @@ void frieda_ctx_destroy(frieda_ctx *ctx) {
 }
 
 const char *frieda_last_error(const frieda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int frieda_ctx_device(const frieda_ctx *ctx) { return ctx ? ctx->device : -1; }
+int frieda_ctx_fail_arg(frieda_ctx *ctx, const char *msg) { return ctx->fail_arg(msg); }
+int frieda_ctx_fail_cuda(frieda_ctx *ctx, int cuda_error, const char *what) {
+  return ctx->fail((cudaError_t)cuda_error, what, 0);
+}
+void frieda_ctx_count_launches(frieda_ctx *ctx, unsigned n) { ctx->launches += n; }
 
 int frieda_ctx_set_workspace_limit(frieda_ctx *ctx, size_t bytes) {
   if (!ctx) return FRIEDA_ERR_ARG;

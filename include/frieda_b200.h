@@ -136,6 +136,13 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
  *      (too few `evaluations`, src/proof.rs:166-173). */
 int frieda_verify(const frieda_proof *proof, const uint64_t *seed_or_null);
 
+/* GPU batch verification: results[i] = 1 / 0 / FRIEDA_ERR_PANIC per proof, same semantics as
+ * frieda_verify.  seeds_or_null: one seed per proof, or NULL when no proof was seeded. */
+int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size_t n, const uint64_t *seeds_or_null,
+                        int *results);
+/* The batch verifier's core run on the host for ONE proof (self-check of the kernels' logic on CPU). */
+int frieda_verify_core_host(const frieda_proof *proof, const uint64_t *seed_or_null);
+
 /* ---- proof objects --------------------------------------------------------------------- */
 void frieda_proof_free(frieda_proof *proof);
 frieda_proof *frieda_proof_clone(const frieda_proof *proof);

@@ -157,3 +157,69 @@ def test_bincode_layout_shape(oracle_proof):
     assert len(b) == want
     assert struct.unpack_from("<Q", b, 0)[0] == c.first_layer.n_fri_witness
     assert struct.unpack_from("<Q", b, len(b) - 8 - 16 * c.n_evaluations)[0] == c.n_evaluations
+
+
+# ---- the GPU batch verifier's core, executed on the host (same __host__ __device__ code as the kernels) ----
+def _core(p, seed):
+    return api.verify_core_host(p, seed)
+
+
+def test_batch_verifier_core_matches_reference_behaviours(oracle_proof):
+    p = F.Proof.deserialize(oracle_proof.serialize())
+    assert _core(p, None) == 1
+    assert _core(p, 7) == 0
+    q = p.clone()
+    q.proof_of_work += 1
+    assert _core(q, None) == 0
+    ev = p.evaluations
+    q = p.clone()
+    q.set_evaluation(0, [(x + 1) % P for x in ev[0]])
+    assert _core(q, None) == 0
+    q = p.clone()
+    for i, e in enumerate(reversed(ev)):
+        q.set_evaluation(i, e)
+    assert _core(q, None) == 0
+    q = p.clone()
+    q.set_evaluation(0, ev[1])
+    q.set_evaluation(1, ev[0])
+    assert _core(q, None) == 0
+    q = p.clone()
+    q.pop_evaluation()
+    assert _core(q, None) == api.ERR_PANIC                       # src/proof.rs:166-173
+    q.c.n_evaluations += 1
+
+
+def test_batch_verifier_core_agrees_with_host_verifier_on_tampering(oracle_proof):
+    p = F.Proof.deserialize(oracle_proof.serialize())
+
+    def both(q, seed=None):
+        try:
+            want = int(F.verify_proof(q, seed))
+        except F.ReferencePanic:
+            want = api.ERR_PANIC
+        assert _core(q, seed) == want
+        return want
+
+    assert both(p) == 1
+    q = p.clone(); q.c.first_layer.hash_witness[5] ^= 1; assert both(q) == 0
+    q = p.clone(); q.c.inner_layers[3].fri_witness[0].v[2] ^= 1; assert both(q) == 0
+    q = p.clone(); q.c.inner_layers[0].commitment[0] ^= 1; assert both(q) == 0
+    q = p.clone(); q.c.last_layer_poly[0].v[0] ^= 1; assert both(q) == 0
+    q = p.clone(); q.c.inner_layers[12].hash_witness[0] ^= 1; assert both(q) == 0
+    q = p.clone(); q.c.n_inner_layers -= 1; assert both(q) == 0; q.c.n_inner_layers += 1
+    q = p.clone(); q.c.first_layer.n_hash_witness -= 1; assert both(q) == 0; q.c.first_layer.n_hash_witness += 1
+    q = p.clone(); q.c.inner_layers[2].n_fri_witness -= 1; assert both(q) == 0; q.c.inner_layers[2].n_fri_witness += 1
+    # Merkle failure in layer 0 together with short evaluations: the rebuild panics first
+    q = p.clone(); q.c.first_layer.hash_witness[0] ^= 1; q.pop_evaluation(); assert both(q) == api.ERR_PANIC
+    q.c.n_evaluations += 1
+
+
+@pytest.mark.parametrize("case", ["pattern_1024_seedlen", "e2e_string", "pattern_3000_b2_l2"])
+def test_batch_verifier_core_other_shapes(case, golden):
+    g = next(x for x in golden["oracle_generated"]["prove"] if x["name"] == case)
+    data = b"This is the original data that needs to be made available." if case == "e2e_string" else bytes(
+        i % 256 for i in range(g["len"]))
+    _, pr = O.prove(data, g["seed"], O.make_config(*g["cfg"]))
+    p = F.Proof.deserialize(pr.serialize())
+    assert _core(p, g["seed"]) == 1
+    assert _core(p, (g["seed"] or 0) + 1) == 0

@@ -553,3 +553,53 @@ def test_commit_config5_64MiB_split_and_unsplit(ctx, torch_mod, golden):
             for r in range(world):
                 ctx.commit_split_local(data, g["log_blowup"], r, world, subs[r].data_ptr())
             assert ctx.merkle_combine(subs.data_ptr(), world).hex() == g["root"], (g["name"], world)
+
+
+# ------------------------------------------------------------------ GPU batch verification
+def test_verify_batch_matches_host_verifier(ctx):
+    cfg = (4, 0, 20, 12)
+    rng = np.random.default_rng(21)
+    n, blob_len = 24, 20000
+    blobs = rng.integers(0, 256, (n, blob_len), dtype=np.uint8)
+    seeds = [1000 + i for i in range(n)]
+    _, proofs = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    cases, case_seeds = [], []
+    for i, p in enumerate(proofs):
+        q = p.clone()
+        kind = i % 8
+        if kind == 1:
+            q.proof_of_work += 1
+        elif kind == 2:
+            q.set_evaluation(0, [(x + 1) % P for x in q.evaluations[0]])
+        elif kind == 3:
+            q.c.inner_layers[1].hash_witness[3] ^= 0x40
+        elif kind == 4:
+            q.c.first_layer.fri_witness[0].v[1] ^= 1
+        elif kind == 5:
+            q.pop_evaluation()
+        elif kind == 6:
+            q.c.last_layer_poly[0].v[3] ^= 2
+        cases.append(q)
+        case_seeds.append(seeds[i] + (1 if kind == 7 else 0))
+    got = ctx.verify_batch(cases, case_seeds)
+    want = []
+    for q, s in zip(cases, case_seeds):
+        try:
+            want.append(int(F.verify_proof(q, s)))
+        except F.ReferencePanic:
+            want.append(-1)
+    assert got == want
+    assert got[0] == 1 and got[8] == 1 and got[16] == 1 and got[1] == 0 and got[5] == -1 and got[7] == 0
+    for q in cases:
+        if q.c.n_evaluations < len(q.evaluations) + 0:
+            pass
+    for i, q in enumerate(cases):
+        if i % 8 == 5:
+            q.c.n_evaluations += 1
+
+
+def test_verify_batch_unseeded_blob_proof(ctx, blob_bytes):
+    _, pr = ctx.commit_and_generate_proof(blob_bytes, None, F.PcsConfig(4, 1, 20, 20))
+    bad = pr.clone()
+    bad.c.inner_layers[7].commitment[31] ^= 0x80
+    assert ctx.verify_batch([pr, bad, pr], None) == [1, 0, 1]
