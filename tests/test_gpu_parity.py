@@ -603,3 +603,71 @@ def test_verify_batch_unseeded_blob_proof(ctx, blob_bytes):
     bad = pr.clone()
     bad.c.inner_layers[7].commitment[31] ^= 0x80
     assert ctx.verify_batch([pr, bad, pr], None) == [1, 0, 1]
+
+
+# ------------------------------------------------------------------ BASELINE config 3 at scale: properties
+def test_c3_batch_properties_full_size_blobs(ctx):
+    # 1024 independent 128 KiB blobs (config 3's blob size; the bench runs 4096 per GPU): size-independent
+    # properties + a sample against the oracle
+    from bench import synth_blobs
+    n = 1024
+    blobs = synth_blobs(n)
+    cfg = F.PcsConfig(4, 0, 20, 20)
+    roots = ctx.commit_batch(blobs, 4)
+    layer_roots, last = ctx.fri_commit_batch(blobs, None, cfg)
+    # (1) first FRI layer commitment == commit() root for every blob (src/proof.rs:126-135)
+    assert np.array_equal(layer_roots[:, 0, :], roots)
+    # (2) idempotence: a second run gives identical bytes
+    layer_roots2, last2 = ctx.fri_commit_batch(blobs, None, cfg)
+    assert np.array_equal(layer_roots, layer_roots2) and np.array_equal(last, last2)
+    # (3) distinct inputs -> distinct commitments on every layer
+    for layer in range(layer_roots.shape[1]):
+        assert len({r.tobytes() for r in layer_roots[:, layer, :]}) == n
+    # (4) a blob's result does not depend on its batch position
+    perm = np.random.default_rng(3).permutation(n)
+    roots_p = ctx.commit_batch(np.ascontiguousarray(blobs[perm]), 4)
+    assert np.array_equal(roots_p, roots[perm])
+    # (5) every value is a canonical M31 element
+    assert int(last.max()) < P
+    # (6) sample against the oracle
+    for b in (0, 511, 1023):
+        oroots, olast = O.fri_commit(blobs[b].tobytes(), None, O.make_config(4, 0, 20, 20))
+        assert [r.tobytes() for r in layer_roots[b]] == oroots
+        assert [tuple(int(x) for x in q) for q in last[b]] == olast
+
+
+# ------------------------------------------------------------------ rarely exercised paths
+def test_commit_device_pointers_unaligned_stride_and_waves(ctx, torch_mod):
+    # odd blob stride (pack kernel's unaligned byte path) and several waves through the device entry point
+    torch = torch_mod
+    rng = np.random.default_rng(31)
+    n, blob_len, stride = 37, 4099, 4101
+    buf = rng.integers(0, 256, n * stride + 7, dtype=np.uint8)
+    d_buf = torch.from_numpy(buf).cuda()
+    d_out = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_workspace_limit(2 * (1 << 20))
+    try:
+        ctx.commit_batch_ptr(d_buf.data_ptr() + 3, blob_len, stride, n, 3, d_out.data_ptr(), device=True)
+        torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    finally:
+        ctx.set_workspace_limit(0)
+    got = d_out.cpu().numpy()
+    for i in (0, 1, 17, 36):
+        data = buf[3 + i * stride: 3 + i * stride + blob_len].tobytes()
+        assert got[i].tobytes() == O.commit(data, 3), i
+
+
+@pytest.mark.parametrize("n_bytes,seed,cfg", [
+    (100, 9, (1, 0, 64, 0)),      # more queries than domain points, pow_bits 0 -> nonce 0
+    (200, None, (2, 1, 40, 2)),
+    (6000, 77, (1, 3, 7, 5)),     # large last layer (log_last 3)
+    (131072, 5, (4, 0, 64, 8)),
+])
+def test_proof_edge_configs_vs_oracle(ctx, n_bytes, seed, cfg):
+    data = pattern(n_bytes)
+    pr = check_proof_vs_oracle(ctx, data, seed, cfg)
+    assert F.verify_proof(pr, seed)
+    assert ctx.verify_batch([pr], None if seed is None else [seed]) == [1]
+    if cfg[3] == 0:
+        assert pr.proof_of_work == 0
