@@ -366,7 +366,7 @@ def main():
     if rank == 0 and not args.no_passes:
         line["passes"] = standalone_passes(ctx, stream, torch, np, hbm_peak, peak_src)
         line["single_blob_latency_ms"] = single_blob_latency(ctx, host_np, cfg)
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cores = os.cpu_count() or 1
         n_threads = max(1, min(cores, 64))
         v1, t1 = cpu_sample(1, 1)

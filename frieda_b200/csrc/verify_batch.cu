@@ -6,6 +6,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/frieda_b200.h"
@@ -108,9 +109,27 @@ int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size
   }
   const uint32_t max_pos = 2 * max_q;
   const size_t blob_bytes = offs[n] * 4;
-  std::vector<uint32_t> words(offs[n]);
-  for (size_t i = 0; i < n; i++)
-    frieda_proof_serialize(proofs[i], reinterpret_cast<uint8_t *>(words.data() + offs[i]), (offs[i + 1] - offs[i]) * 4);
+  // serialise straight into pinned memory, on a few host threads
+  uint32_t *words = nullptr;
+  if ((e = cudaHostAlloc(reinterpret_cast<void **>(&words), blob_bytes ? blob_bytes : 4, cudaHostAllocDefault)) !=
+      cudaSuccess)
+    return frieda_ctx_fail_cuda(ctx, (int)e, "cudaHostAlloc(verify batch)");
+  {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    if (n < 64) nt = 1;
+    auto work = [&](unsigned t) {
+      for (size_t i = t; i < n; i += nt)
+        frieda_proof_serialize(proofs[i], reinterpret_cast<uint8_t *>(words + offs[i]), (offs[i + 1] - offs[i]) * 4);
+    };
+    if (nt == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+      for (auto &x : th) x.join();
+    }
+  }
   // device buffers
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t o_blob = 0, o_offs = o_blob + al(blob_bytes), o_seeds = o_offs + al((n + 1) * 8);
@@ -119,11 +138,14 @@ int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size
   size_t o_ev = o_q + al(n * (size_t)max_q * 4), o_al = o_ev + al(n * (size_t)max_q * sizeof(QM31));
   size_t total = o_al + al(n * (size_t)V_MAX_LAYERS * sizeof(QM31));
   uint8_t *d = nullptr;
-  if ((e = cudaMalloc(&d, total)) != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "cudaMalloc(verify batch)");
+  if ((e = cudaMalloc(&d, total)) != cudaSuccess) {
+    cudaFreeHost(words);
+    return frieda_ctx_fail_cuda(ctx, (int)e, "cudaMalloc(verify batch)");
+  }
   int rc = FRIEDA_OK;
   std::vector<VProofState> h_st(n);
   do {
-    if ((e = cudaMemcpyAsync(d + o_blob, words.data(), blob_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d + o_blob, words, blob_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
     if ((e = cudaMemcpyAsync(d + o_offs, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
     if (seeds_or_null &&
         (e = cudaMemcpyAsync(d + o_seeds, seeds_or_null, n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
@@ -147,6 +169,7 @@ int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size
     e = cudaStreamSynchronize(st);
   } while (0);
   cudaFree(d);
+  cudaFreeHost(words);
   if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "frieda_verify_batch");
   for (size_t i = 0; i < n; i++) results[i] = verify_resolve(h_st[i]);
   return rc;
