@@ -24,14 +24,14 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t *__restrict__ 
                                                     uint32_t *__restrict__ dst, size_t dst_stride) {
   const size_t blob = blockIdx.y;
   const size_t n = (size_t)1 << dst_log;
-  const QM31 al = alpha[blob * alpha_stride];
+  const QM31Mat amat = qm31_mat(alpha[blob * alpha_stride]);
   const uint2 *s = reinterpret_cast<const uint2 *>(src + blob * src_stride);
   uint32_t *d = dst + blob * dst_stride;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint2 e0 = __ldg(s + i), e1 = __ldg(s + n + i), e2 = __ldg(s + 2 * n + i), e3 = __ldg(s + 3 * n + i);
     QM31 a = {{e0.x, e1.x, e2.x, e3.x}}, b = {{e0.y, e1.y, e2.y, e3.y}};
     uint32_t itw = is_circle ? circle_fold_itw_(iblk, i) : __ldg(iblk + i);
-    QM31 f = fri_fold_pair(a, b, itw, al);
+    QM31 f = fri_fold_pair_mat(a, b, itw, amat);
     d[i] = f.v[0];
     d[n + i] = f.v[1];
     d[2 * n + i] = f.v[2];
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
       s_alpha = a;
     }
     __syncthreads();
-    const QM31 al = s_alpha;
+    const QM31Mat amat = qm31_mat(s_alpha);
     // fold into the next layer
     const uint32_t nn = n >> 1;
     uint32_t *dst = p.cols[layer + 1] + blob * p.cols_stride[layer + 1];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
       QM31 b = {{s_cols[cur][0][2 * i + 1], s_cols[cur][1][2 * i + 1], s_cols[cur][2][2 * i + 1],
                  s_cols[cur][3][2 * i + 1]}};
       uint32_t itw = layer == 0 ? circle_fold_itw_(iblk, i) : __ldg(iblk + i);
-      QM31 f = fri_fold_pair(a, b, itw, al);
+      QM31 f = fri_fold_pair_mat(a, b, itw, amat);
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         s_cols[cur ^ 1][c][i] = f.v[c];

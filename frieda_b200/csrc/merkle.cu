@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleB
     for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) sm_a[j] = src[j];
   } else {
     const size_t n = (size_t)1 << p.log;
-    QM31 alpha;
-    if (SRC == SRC_FOLD_CIRCLE || SRC == SRC_FOLD_LINE) alpha = p.alpha[blob * p.alpha_stride];
+    QM31Mat amat;  // multiplication by this blob's folding alpha as a 4x4 matrix (m31.cuh)
+    if (SRC == SRC_FOLD_CIRCLE || SRC == SRC_FOLD_LINE) amat = qm31_mat(p.alpha[blob * p.alpha_stride]);
     for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
       const size_t i = leaf0 + j;
       uint32_t c0, c1, c2, c3;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleB
         uint2 e0 = __ldg(s), e1 = __ldg(s + n), e2 = __ldg(s + 2 * n), e3 = __ldg(s + 3 * n);
         QM31 a = {{e0.x, e1.x, e2.x, e3.x}}, b = {{e0.y, e1.y, e2.y, e3.y}};
         uint32_t itw = SRC == SRC_FOLD_CIRCLE ? circle_fold_itw(p.itw_blk, i) : __ldg(p.itw_blk + i);
-        QM31 f = fri_fold_pair(a, b, itw, alpha);
+        QM31 f = fri_fold_pair_mat(a, b, itw, amat);
         c0 = f.v[0];
         c1 = f.v[1];
         c2 = f.v[2];
