@@ -167,7 +167,21 @@ __device__ __forceinline__ void last_pass(const uint32_t *__restrict__ src, bool
   // line layers R-1 .. 1
   line_stages<R, R - 1>(v, tt, K, p, hb, R - 1, g);
   // circle layer
-  {
+  if (R >= 3) {
+    // N/2 consecutive circle twiddles starting at a multiple of 4: the [y, -y, -x, x] pattern is static
+    const uint32_t *tw0 = tt.blk(1u << (K - 1));
+    const uint32_t h_base = (hb << (p - 1)) + (g << (R - 1));
+    const uint2 *xy = reinterpret_cast<const uint2 *>(tw0) + (h_base >> 2);
+#pragma unroll
+    for (int m = 0; m < N / 8; m++) {
+      const uint2 q = __ldg(xy + m);  // (x, y)
+      const uint32_t y2 = q.y + q.y, ny2 = 2 * m31_neg(q.y), nx2 = 2 * m31_neg(q.x), x2 = q.x + q.x;
+      bfly_t2(v[8 * m + 0], v[8 * m + 1], y2);
+      bfly_t2(v[8 * m + 2], v[8 * m + 3], ny2);
+      bfly_t2(v[8 * m + 4], v[8 * m + 5], nx2);
+      bfly_t2(v[8 * m + 6], v[8 * m + 7], x2);
+    }
+  } else {
     const uint32_t *tw0 = tt.blk(1u << (K - 1));
     const uint32_t h_base = (hb << (p - 1)) + (g << (R - 1));
 #pragma unroll
@@ -196,37 +210,38 @@ __device__ __forceinline__ void last_pass(const uint32_t *__restrict__ src, bool
   }
 }
 
-// One radix-16 pass over layers LO+3 .. LO with every index compile-time: the 16 shared-memory
+// One radix-2^R pass over layers LO+R-1 .. LO with every index compile-time: the 2^R shared-memory
 // slots of a group are one computed address plus immediates.
-template <int P, int LO, bool FROM_GLOBAL, int THREADS>
-__device__ __forceinline__ void r16_pass(const uint32_t *__restrict__ c, uint32_t *sm, const TwiddleTable &tt,
-                                         uint32_t K, uint32_t hb) {
-  // twiddle rows of the 4 layers, offset to this block (warp-uniform)
-  const uint32_t *row[4];
+template <int P, int LO, int R, bool FROM_GLOBAL, int THREADS>
+__device__ __forceinline__ void rn_pass(const uint32_t *__restrict__ c, uint32_t *sm, const TwiddleTable &tt,
+                                        uint32_t K, uint32_t hb) {
+  constexpr int N = 1 << R;
+  // twiddle rows of the R layers, offset to this block (warp-uniform)
+  const uint32_t *row[R];
 #pragma unroll
-  for (int s = 0; s < 4; s++) {
-    const int i = LO + 3 - s;
+  for (int s = 0; s < R; s++) {
+    const int i = LO + R - 1 - s;
     row[s] = tt.blk(1u << (K - i)) + ((size_t)hb << (P - i - 1));
   }
   // padded offset of element j from element 0: the group's low bits never carry into bit 6
   auto off = [](int j) -> uint32_t { return ((uint32_t)j << LO) + ((((uint32_t)j << LO) >> 6) << 2); };
 #pragma unroll 1
-  for (uint32_t g = threadIdx.x; g < (1u << (P - 4)); g += THREADS) {
+  for (uint32_t g = threadIdx.x; g < (1u << (P - R)); g += THREADS) {
     const uint32_t lower = g & ((1u << LO) - 1), upper = g >> LO;
-    const uint32_t base = (upper << (LO + 4)) | lower;
+    const uint32_t base = (upper << (LO + R)) | lower;
     uint32_t *slot = sm + padi(base);
-    uint32_t v[16];
+    uint32_t v[N];
     if (FROM_GLOBAL) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) v[j] = __ldg(c + base + ((uint32_t)j << LO));
+      for (int j = 0; j < N; j++) v[j] = __ldg(c + base + ((uint32_t)j << LO));
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; j++) v[j] = slot[off(j)];
+      for (int j = 0; j < N; j++) v[j] = slot[off(j)];
     }
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
+    for (int s = 0; s < R; s++) {
       const uint32_t *tw = row[s] + ((size_t)upper << s);
-      const int half = 8 >> s;
+      const int half = N >> (s + 1);
 #pragma unroll
       for (int q = 0; q < (1 << s); q++) {
         uint32_t t = __ldg(tw + q);
@@ -236,14 +251,29 @@ __device__ __forceinline__ void r16_pass(const uint32_t *__restrict__ c, uint32_
       }
     }
 #pragma unroll
-    for (int j = 0; j < 16; j++) slot[off(j)] = v[j];
+    for (int j = 0; j < N; j++) slot[off(j)] = v[j];
   }
 }
+
+// Pass schedule for a 2^P-point block: a last pass of R_LAST layers on consecutive points, and the
+// P - R_LAST layers above it split as evenly as possible into passes of at most MAXR layers.
+template <int P, int MAXR>
+struct LdeSched {
+  static constexpr int R_LAST = P >= 4 ? 4 : P;
+  static constexpr int REM = P - R_LAST;
+  static constexpr int NP = (REM + MAXR - 1) / MAXR;
+  static constexpr int r(int k) { return NP == 0 ? 0 : REM / NP + (k < REM % NP ? 1 : 0); }
+  static constexpr int lo(int k) {  // lowest layer of pass k
+    int top = P;
+    for (int i = 0; i <= k; i++) top -= r(i);
+    return top;
+  }
+};
 
 // INPLACE: the block is a 2^P chunk of an evaluation array that already went through the layers
 // above P (large polynomials); it is read from and written back to `eval`, and `p_full` is the
 // true poly_log (for the zero-column test and the twiddle geometry D = p_full + beta).
-template <int P, int THREADS, bool INPLACE>
+template <int P, int THREADS, bool INPLACE, int MAXR = 4>
 __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *coef, uint32_t *eval, uint32_t beta,
                                                             uint32_t n_felts, TwiddleTable tt, LdeRange rg,
                                                             uint32_t p_full) {
@@ -265,24 +295,25 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *coef
     for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
     return;
   }
-  constexpr int R_LAST = ((P - 1) & 3) + 1;
-  constexpr int N_R16 = (P - R_LAST) >> 2;
-  if (N_R16 >= 1) {
-    r16_pass<P, (P >= 4 ? P - 4 : 0), true, THREADS>(c, sm, tt, K, hb);
+  using S = LdeSched<P, MAXR>;
+  constexpr int R_LAST = S::R_LAST;
+  if constexpr (S::NP >= 1) {
+    rn_pass<P, S::lo(0), S::r(0), true, THREADS>(c, sm, tt, K, hb);
     __syncthreads();
   }
-  if (N_R16 >= 2) {
-    r16_pass<P, (P >= 8 ? P - 8 : 0), false, THREADS>(c, sm, tt, K, hb);
+  if constexpr (S::NP >= 2) {
+    rn_pass<P, S::lo(1), S::r(1), false, THREADS>(c, sm, tt, K, hb);
     __syncthreads();
   }
-  if (N_R16 >= 3) {
-    r16_pass<P, (P >= 12 ? P - 12 : 0), false, THREADS>(c, sm, tt, K, hb);
+  if constexpr (S::NP >= 3) {
+    rn_pass<P, S::lo(2), S::r(2), false, THREADS>(c, sm, tt, K, hb);
     __syncthreads();
   }
-  const uint32_t *src = N_R16 ? sm : c;
+  static_assert(S::NP <= 3, "schedule needs more passes than the kernel unrolls");
+  const uint32_t *src = S::NP ? sm : c;
 #pragma unroll 1
   for (uint32_t g = threadIdx.x; g < (n4 >> R_LAST); g += THREADS)
-    last_pass<R_LAST>(src, N_R16 != 0, out, g, tt, K, p, hb, w_lo, w_n, full);
+    last_pass<R_LAST>(src, S::NP != 0, out, g, tt, K, p, hb, w_lo, w_n, full);
 }
 
 // poly_log 0: one coefficient per column; every layer is a replication.
@@ -399,14 +430,15 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
   static bool attr_set = false;
   const int big = (4 << LDE_SMEM_LOG_MAX) + (4 << LDE_SMEM_LOG_MAX) / 16 + 64;
   if (!attr_set) {
-    cudaFuncSetAttribute(lde_block_kernel<12, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<13, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<14, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<12, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<13, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<14, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    // blocks of 2^12 .. 2^15 points: passes of up to 5 layers (radix 32) with 256 threads measured fastest
+    cudaFuncSetAttribute(lde_block_kernel<12, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<13, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<14, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<12, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<13, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<14, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_set = true;
   }
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
@@ -418,14 +450,17 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       size_t smem = ((size_t)4 << p) + (((size_t)4 << p) >> 4) + 64;  // + 4 pad words per 64
 #define FR_LDE_CASE(PP, TT) \
   case PP: lde_block_kernel<PP, TT, false><<<grid, TT, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+#define FR_LDE_BIG(PP) \
+  case PP: lde_block_kernel<PP, 256, false, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
       switch (p) {
         case 0: lde_copy_kernel<<<grid, 1, 0, st>>>(cf, ev, beta, n_felts, rg); break;
         FR_LDE_CASE(1, 32) FR_LDE_CASE(2, 32) FR_LDE_CASE(3, 32) FR_LDE_CASE(4, 32) FR_LDE_CASE(5, 32)
         FR_LDE_CASE(6, 32) FR_LDE_CASE(7, 64) FR_LDE_CASE(8, 64) FR_LDE_CASE(9, 128) FR_LDE_CASE(10, 128)
-        FR_LDE_CASE(11, 256) FR_LDE_CASE(12, 512) FR_LDE_CASE(13, 512) FR_LDE_CASE(14, 512) FR_LDE_CASE(15, 512)
+        FR_LDE_CASE(11, 256) FR_LDE_BIG(12) FR_LDE_BIG(13) FR_LDE_BIG(14) FR_LDE_BIG(15)
         default: return cudaErrorInvalidValue;
       }
 #undef FR_LDE_CASE
+#undef FR_LDE_BIG
     } else {
       // m register-only radix-16 passes over layers p-1 .. c, then 2^c chunks in shared memory;
       // c = p - 4m lies in 12..15.  After the first pass everything stays inside the owned range.
@@ -446,10 +481,10 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
       size_t smem = ((size_t)4 << c) + (((size_t)4 << c) >> 4) + 64;
       switch (c) {
-        case 12: lde_block_kernel<12, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        case 13: lde_block_kernel<13, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        case 14: lde_block_kernel<14, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        default: lde_block_kernel<15, 512, true><<<grid, 512, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        case 12: lde_block_kernel<12, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        case 13: lde_block_kernel<13, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        case 14: lde_block_kernel<14, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        default: lde_block_kernel<15, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
       }
     }
   }
