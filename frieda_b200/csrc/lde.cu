@@ -434,11 +434,12 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     cudaFuncSetAttribute(lde_block_kernel<12, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_block_kernel<13, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_block_kernel<14, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    // 2^15-point blocks take 136 KiB of shared memory (one CTA per SM): 1024 threads, radix-16 passes
+    cudaFuncSetAttribute(lde_block_kernel<15, 1024, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_block_kernel<12, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_block_kernel<13, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(lde_block_kernel<14, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(lde_block_kernel<15, 1024, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_set = true;
   }
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
@@ -456,7 +457,8 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
         case 0: lde_copy_kernel<<<grid, 1, 0, st>>>(cf, ev, beta, n_felts, rg); break;
         FR_LDE_CASE(1, 32) FR_LDE_CASE(2, 32) FR_LDE_CASE(3, 32) FR_LDE_CASE(4, 32) FR_LDE_CASE(5, 32)
         FR_LDE_CASE(6, 32) FR_LDE_CASE(7, 64) FR_LDE_CASE(8, 64) FR_LDE_CASE(9, 128) FR_LDE_CASE(10, 128)
-        FR_LDE_CASE(11, 256) FR_LDE_BIG(12) FR_LDE_BIG(13) FR_LDE_BIG(14) FR_LDE_BIG(15)
+        FR_LDE_CASE(11, 256) FR_LDE_BIG(12) FR_LDE_BIG(13) FR_LDE_BIG(14)
+        case 15: lde_block_kernel<15, 1024, false, 4><<<grid, 1024, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
         default: return cudaErrorInvalidValue;
       }
 #undef FR_LDE_CASE
@@ -484,7 +486,7 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
         case 12: lde_block_kernel<12, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
         case 13: lde_block_kernel<13, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
         case 14: lde_block_kernel<14, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        default: lde_block_kernel<15, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        default: lde_block_kernel<15, 1024, true, 4><<<grid, 1024, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
       }
     }
   }
