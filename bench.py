@@ -455,9 +455,31 @@ def extras(ctx, host_np, cfg, torch):
     t0 = time.perf_counter()
     host_ok = all(F.verify_proof(proofs[i], seeds[i]) for i in range(32))
     dth = (time.perf_counter() - t0) / 32
-    out["verify_batch"] = {"proofs": len(many), "all_valid": all(r == 1 for r in res) and host_ok,
-                           "proofs_per_s": len(many) / dtv, "host_verifier_proofs_per_s_1_thread": 1.0 / dth,
-                           "note": "wall clock incl. host serialisation + H2D of the proofs (132 KB each)"}
+    # same proofs as serialised bytes (what a light client holds): kernels timed with CUDA events
+    import numpy as np
+    pieces = [p.serialize() for p in proofs]
+    offs1 = np.concatenate([[0], np.cumsum([len(b) for b in pieces])]).astype(np.uint64)
+    reps = (4096 + npv - 1) // npv
+    blob = torch.from_numpy(np.tile(np.frombuffer(b"".join(pieces), dtype=np.uint8), reps)).pin_memory().numpy()
+    offs = np.concatenate([offs1[:-1] + r * offs1[-1] for r in range(reps)] + [[reps * offs1[-1]]]).astype(np.uint64)
+    sb = (seeds * reps)
+    ctx.verify_batch_bytes(blob, offs, sb)
+    ctx.profile_read(reset=True)
+    ctx.set_profiling(True)
+    t0 = time.perf_counter()
+    resb = ctx.verify_batch_bytes(blob, offs, sb)
+    dtb = time.perf_counter() - t0
+    ctx.set_profiling(False)
+    vprof = ctx.profile_read(reset=True)
+    kern_ms = sum(v[1] for v in vprof.values())
+    out["verify_batch"] = {"proofs": len(many), "all_valid": all(r == 1 for r in res) and all(r == 1 for r in resb)
+                           and host_ok,
+                           "proofs_per_s_from_structs": len(many) / dtv, "proofs_per_s_from_bytes": len(resb) / dtb,
+                           "kernel_ms": {k: round(v[1], 3) for k, v in vprof.items()},
+                           "proofs_per_s_kernels_only": len(resb) / (kern_ms / 1e3) if kern_ms else None,
+                           "proof_bytes_total": int(offs[-1]),
+                           "host_verifier_proofs_per_s_1_thread": 1.0 / dth,
+                           "note": "wall clock incl. upload of the proofs (132 KB each); from_structs also serialises"}
     out["prove_c4_e2e"] = {"blobs": npv, "n_queries": 64, "pow_bits": CFG[3], "blobs_per_s": npv / dt,
                            "proofs_verify": ok, "wall_ms": dt * 1e3,
                            "kernel_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},

@@ -89,6 +89,7 @@ EXPORTS = [
     "frieda_ctx_launch_count", "frieda_ctx_stream", "frieda_ctx_set_profiling", "frieda_ctx_profile_read", "frieda_commit", "frieda_commit_batch",
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
     "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_verify_batch",
+    "frieda_verify_batch_bytes",
     "frieda_verify_core_host", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device",
@@ -134,6 +135,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_prove_batch": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, C.POINTER(pp)]),
         "frieda_verify": (C.c_int, [pp, u64p]),
         "frieda_verify_batch": (C.c_int, [vp, C.POINTER(pp), sz, vp, C.POINTER(C.c_int)]),
+        "frieda_verify_batch_bytes": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(C.c_int)]),
         "frieda_verify_core_host": (C.c_int, [pp, u64p]),
         "frieda_proof_free": (None, [pp]),
         "frieda_proof_clone": (pp, [pp]),
@@ -411,6 +413,20 @@ class Context:
             sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
             assert sd.shape == (n,)
         self._check(self._L.frieda_verify_batch(self._h, arr, n, sd.ctypes.data if sd is not None else None, res))
+        return [int(x) for x in res]
+
+    def verify_batch_bytes(self, blob: np.ndarray, byte_offsets: np.ndarray, seeds: Optional[Sequence[int]]) -> List[int]:
+        """GPU batch verification of serialised proofs: blob = concatenated Proof.serialize() outputs (uint8,
+        4-byte aligned pieces), byte_offsets = n + 1 uint64 offsets."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs = np.ascontiguousarray(byte_offsets, dtype=np.uint64)
+        n = len(offs) - 1
+        res = (C.c_int * n)()
+        sd = None
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        self._check(self._L.frieda_verify_batch_bytes(self._h, blob.ctypes.data, offs.ctypes.data, n,
+                                                      sd.ctypes.data if sd is not None else None, res))
         return [int(x) for x in res]
 
     # -- split blob ----------------------------------------------------------------

@@ -921,6 +921,8 @@ int frieda_ctx_fail_cuda(frieda_ctx *ctx, int cuda_error, const char *what) {
   return ctx->fail((cudaError_t)cuda_error, what, 0);
 }
 void frieda_ctx_count_launches(frieda_ctx *ctx, unsigned n) { ctx->launches += n; }
+void frieda_ctx_prof_begin(frieda_ctx *ctx, const char *name) { ctx->prof_begin(name); }
+void frieda_ctx_prof_end(frieda_ctx *ctx) { ctx->prof_end(); }
 
 int frieda_ctx_set_workspace_limit(frieda_ctx *ctx, size_t bytes) {
   if (!ctx) return FRIEDA_ERR_ARG;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(64) verify_phase_a_kernel(const uint32_t *__re
   uint64_t seed = seeds ? seeds[i] : 0;
   verify_phase_a(blob + offs[i], (uint32_t)(offs[i + 1] - offs[i]), seeds ? &seed : nullptr, gp, st[i],
                  leaves + i * (size_t)n_layers_max * max_pos, max_pos, queries + i * (size_t)max_q, max_q,
-                 evals + i * (size_t)max_q, alphas + i * (size_t)V_MAX_LAYERS);
+                 evals + i * (size_t)max_q, alphas + i * (size_t)V_MAX_LAYERS, n_layers_max);
 }
 
 __global__ void __launch_bounds__(64) verify_phase_b_kernel(const uint32_t *__restrict__ blob,
@@ -85,15 +85,106 @@ int frieda_verify_core_host(const frieda_proof *proof, const uint64_t *seed_or_n
   return verify_resolve(st);
 }
 
+}  // extern "C"
+
+// Common path: `words` = concatenated FRDA encodings (host memory, ideally pinned), offs = word offsets.
+static int verify_batch_words(frieda_ctx *ctx, const uint32_t *words, const std::vector<unsigned long long> &offs,
+                              size_t n, uint32_t n_layers_max, uint32_t max_q, const uint64_t *seeds_or_null,
+                              int *results) {
+  cudaError_t e = cudaSetDevice(frieda_ctx_device(ctx));
+  if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "cudaSetDevice");
+  cudaStream_t st = (cudaStream_t)frieda_ctx_stream(ctx);
+  const uint32_t max_pos = 2 * max_q;
+  const size_t blob_bytes = offs[n] * 4;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o_blob = 0, o_offs = o_blob + al(blob_bytes), o_seeds = o_offs + al((n + 1) * 8);
+  size_t o_st = o_seeds + al(n * 8), o_leaves = o_st + al(n * sizeof(VProofState));
+  size_t o_q = o_leaves + al(n * (size_t)n_layers_max * max_pos * sizeof(VNode));
+  size_t o_ev = o_q + al(n * (size_t)max_q * 4), o_al = o_ev + al(n * (size_t)max_q * sizeof(QM31));
+  size_t total = o_al + al(n * (size_t)V_MAX_LAYERS * sizeof(QM31));
+  uint8_t *d = nullptr;
+  if ((e = cudaMalloc(&d, total)) != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "cudaMalloc(verify batch)");
+  std::vector<VProofState> h_st(n);
+  do {
+    if ((e = cudaMemcpyAsync(d + o_blob, words, blob_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d + o_offs, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if (seeds_or_null &&
+        (e = cudaMemcpyAsync(d + o_seeds, seeds_or_null, n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      break;
+    VGen gp = make_gen();
+    frieda_ctx_prof_begin(ctx, "verify_phase_a");
+    verify_phase_a_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(d + o_blob), reinterpret_cast<const unsigned long long *>(d + o_offs),
+        seeds_or_null ? reinterpret_cast<const unsigned long long *>(d + o_seeds) : nullptr, gp,
+        reinterpret_cast<VProofState *>(d + o_st), reinterpret_cast<VNode *>(d + o_leaves), n_layers_max, max_pos,
+        reinterpret_cast<uint32_t *>(d + o_q), max_q, reinterpret_cast<QM31 *>(d + o_ev),
+        reinterpret_cast<QM31 *>(d + o_al), n);
+    frieda_ctx_prof_end(ctx);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    size_t nt = n * n_layers_max;
+    frieda_ctx_prof_begin(ctx, "verify_phase_b");
+    verify_phase_b_kernel<<<(unsigned)((nt + 63) / 64), 64, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(d + o_blob), reinterpret_cast<const unsigned long long *>(d + o_offs),
+        reinterpret_cast<VProofState *>(d + o_st), reinterpret_cast<VNode *>(d + o_leaves), n_layers_max, max_pos, n);
+    frieda_ctx_prof_end(ctx);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    frieda_ctx_count_launches(ctx, 2);
+    if ((e = cudaMemcpyAsync(h_st.data(), d + o_st, n * sizeof(VProofState), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  cudaFree(d);
+  if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "frieda_verify_batch");
+  for (size_t i = 0; i < n; i++) results[i] = verify_resolve(h_st[i]);
+  return FRIEDA_OK;
+}
+
+extern "C" int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
+                                         const uint64_t *seeds_or_null, int *results);
+// Serialised proofs (frieda_proof_serialize encoding), proof i at bytes + byte_offsets[i] .. byte_offsets[i+1];
+// offsets must be multiples of 4.  This is what a light client holds after receiving proofs.
+int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
+                              const uint64_t *seeds_or_null, int *results) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!bytes || !byte_offsets || !results) return frieda_ctx_fail_arg(ctx, "null pointer");
+  if (n == 0) return FRIEDA_OK;
+  if ((reinterpret_cast<uintptr_t>(bytes) & 3) != 0) return frieda_ctx_fail_arg(ctx, "proof bytes must be 4-byte aligned");
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(bytes);
+  std::vector<unsigned long long> offs(n + 1);
+  uint32_t n_layers_max = 1, max_q = 1;
+  for (size_t i = 0; i <= n; i++) {
+    if (byte_offsets[i] & 3) return frieda_ctx_fail_arg(ctx, "proof offsets must be multiples of 4");
+    offs[i] = byte_offsets[i] / 4;
+    if (i && offs[i] < offs[i - 1]) return frieda_ctx_fail_arg(ctx, "proof offsets must be non-decreasing");
+  }
+  for (size_t i = 0; i < n; i++) {
+    // header: magic, log_size_bound, log_blowup, log_last, n_queries (u64), pow_bits, pow (u64), n_evals, ...
+    const uint32_t *w = words + offs[i];
+    const size_t len = offs[i + 1] - offs[i];
+    uint32_t nq = 1, nl = 1;
+    if (len > 10) {
+      nq = w[5] ? 4097u : w[4];
+      size_t pos = 10 + 4 * (size_t)w[9];
+      if (pos < len) {
+        pos += 1 + 4 * (size_t)w[pos];
+        if (pos < len) nl = w[pos];
+      }
+    }
+    if (nq > 4096) nq = 4096;  // phase A rejects proofs that do not fit the batch capacity
+    if (nl > V_MAX_LAYERS) nl = V_MAX_LAYERS;
+    max_q = nq > max_q ? nq : max_q;
+    n_layers_max = nl > n_layers_max ? nl : n_layers_max;
+  }
+  return verify_batch_words(ctx, words, offs, n, n_layers_max, max_q, seeds_or_null, results);
+}
+
+extern "C" {
+
 int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size_t n, const uint64_t *seeds_or_null,
                         int *results) {
   if (!ctx) return FRIEDA_ERR_ARG;
   if (!proofs || !results) return frieda_ctx_fail_arg(ctx, "null pointer");
   if (n == 0) return FRIEDA_OK;
-  cudaError_t e = cudaSetDevice(frieda_ctx_device(ctx));
-  if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "cudaSetDevice");
-  cudaStream_t st = (cudaStream_t)frieda_ctx_stream(ctx);
-  // flat encoding of all proofs, word offsets
   std::vector<unsigned long long> offs(n + 1, 0);
   uint32_t n_layers_max = 1, max_q = 1;
   for (size_t i = 0; i < n; i++) {
@@ -107,13 +198,11 @@ int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size
     uint32_t q = (uint32_t)proofs[i]->pcs_config.n_queries;
     max_q = q > max_q ? q : max_q;
   }
-  const uint32_t max_pos = 2 * max_q;
   const size_t blob_bytes = offs[n] * 4;
   // serialise straight into pinned memory, on a few host threads
   uint32_t *words = nullptr;
-  if ((e = cudaHostAlloc(reinterpret_cast<void **>(&words), blob_bytes ? blob_bytes : 4, cudaHostAllocDefault)) !=
-      cudaSuccess)
-    return frieda_ctx_fail_cuda(ctx, (int)e, "cudaHostAlloc(verify batch)");
+  cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&words), blob_bytes ? blob_bytes : 4, cudaHostAllocDefault);
+  if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "cudaHostAlloc(verify batch)");
   {
     unsigned nt = std::thread::hardware_concurrency();
     nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
@@ -130,48 +219,8 @@ int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size
       for (auto &x : th) x.join();
     }
   }
-  // device buffers
-  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-  size_t o_blob = 0, o_offs = o_blob + al(blob_bytes), o_seeds = o_offs + al((n + 1) * 8);
-  size_t o_st = o_seeds + al(n * 8), o_leaves = o_st + al(n * sizeof(VProofState));
-  size_t o_q = o_leaves + al(n * (size_t)n_layers_max * max_pos * sizeof(VNode));
-  size_t o_ev = o_q + al(n * (size_t)max_q * 4), o_al = o_ev + al(n * (size_t)max_q * sizeof(QM31));
-  size_t total = o_al + al(n * (size_t)V_MAX_LAYERS * sizeof(QM31));
-  uint8_t *d = nullptr;
-  if ((e = cudaMalloc(&d, total)) != cudaSuccess) {
-    cudaFreeHost(words);
-    return frieda_ctx_fail_cuda(ctx, (int)e, "cudaMalloc(verify batch)");
-  }
-  int rc = FRIEDA_OK;
-  std::vector<VProofState> h_st(n);
-  do {
-    if ((e = cudaMemcpyAsync(d + o_blob, words, blob_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync(d + o_offs, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-    if (seeds_or_null &&
-        (e = cudaMemcpyAsync(d + o_seeds, seeds_or_null, n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-      break;
-    VGen gp = make_gen();
-    verify_phase_a_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(
-        reinterpret_cast<const uint32_t *>(d + o_blob), reinterpret_cast<const unsigned long long *>(d + o_offs),
-        seeds_or_null ? reinterpret_cast<const unsigned long long *>(d + o_seeds) : nullptr, gp,
-        reinterpret_cast<VProofState *>(d + o_st), reinterpret_cast<VNode *>(d + o_leaves), n_layers_max, max_pos,
-        reinterpret_cast<uint32_t *>(d + o_q), max_q, reinterpret_cast<QM31 *>(d + o_ev),
-        reinterpret_cast<QM31 *>(d + o_al), n);
-    if ((e = cudaGetLastError()) != cudaSuccess) break;
-    size_t nt = n * n_layers_max;
-    verify_phase_b_kernel<<<(unsigned)((nt + 63) / 64), 64, 0, st>>>(
-        reinterpret_cast<const uint32_t *>(d + o_blob), reinterpret_cast<const unsigned long long *>(d + o_offs),
-        reinterpret_cast<VProofState *>(d + o_st), reinterpret_cast<VNode *>(d + o_leaves), n_layers_max, max_pos, n);
-    if ((e = cudaGetLastError()) != cudaSuccess) break;
-    frieda_ctx_count_launches(ctx, 2);
-    if ((e = cudaMemcpyAsync(h_st.data(), d + o_st, n * sizeof(VProofState), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-      break;
-    e = cudaStreamSynchronize(st);
-  } while (0);
-  cudaFree(d);
+  int rc = verify_batch_words(ctx, words, offs, n, n_layers_max, max_q, seeds_or_null, results);
   cudaFreeHost(words);
-  if (e != cudaSuccess) return frieda_ctx_fail_cuda(ctx, (int)e, "frieda_verify_batch");
-  for (size_t i = 0; i < n; i++) results[i] = verify_resolve(h_st[i]);
   return rc;
 }
 

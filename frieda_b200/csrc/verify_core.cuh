@@ -78,7 +78,8 @@ FR_HD QM31 v_q(const uint32_t *p) { return {{p[0], p[1], p[2], p[3]}}; }
 // Phase A.  `leaves` holds max_pos entries per layer (layer-major); max_q = capacity of `queries`.
 FR_HD void verify_phase_a(const uint32_t *words, uint32_t n_words, const uint64_t *seed, const VGen &gp,
                           VProofState &st, VNode *leaves, uint32_t max_pos, uint32_t *queries, uint32_t max_q,
-                          QM31 *evals /* max_q */, QM31 *alphas /* V_MAX_LAYERS */) {
+                          QM31 *evals /* max_q */, QM31 *alphas /* V_MAX_LAYERS */,
+                          uint32_t max_layers = V_MAX_LAYERS) {
   st.a_kind = 1;
   st.a_layer = 0;
   st.a_post = 0;
@@ -105,7 +106,7 @@ FR_HD void verify_phase_a(const uint32_t *words, uint32_t n_words, const uint64_
   const uint32_t n_last = r.u32();
   const uint32_t *last = r.take(4 * n_last);
   const uint32_t n_layers = r.u32();
-  if (!r.ok || n_layers == 0 || n_layers > V_MAX_LAYERS) return stop(0, 0, 0);
+  if (!r.ok || n_layers == 0 || n_layers > V_MAX_LAYERS || n_layers > max_layers) return stop(0, 0, 0);
   st.n_layers = n_layers;
   // locate the layers
   const uint32_t *commit[V_MAX_LAYERS];

@@ -140,6 +140,10 @@ int frieda_verify(const frieda_proof *proof, const uint64_t *seed_or_null);
  * frieda_verify.  seeds_or_null: one seed per proof, or NULL when no proof was seeded. */
 int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size_t n, const uint64_t *seeds_or_null,
                         int *results);
+/* Same over SERIALISED proofs (frieda_proof_serialize encoding): proof i occupies bytes[byte_offsets[i] ..
+ * byte_offsets[i+1]); `bytes` and all offsets 4-byte aligned, n + 1 offsets. */
+int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
+                              const uint64_t *seeds_or_null, int *results);
 /* The batch verifier's core run on the host for ONE proof (self-check of the kernels' logic on CPU). */
 int frieda_verify_core_host(const frieda_proof *proof, const uint64_t *seed_or_null);
 

@@ -671,3 +671,26 @@ def test_proof_edge_configs_vs_oracle(ctx, n_bytes, seed, cfg):
     assert ctx.verify_batch([pr], None if seed is None else [seed]) == [1]
     if cfg[3] == 0:
         assert pr.proof_of_work == 0
+
+
+def test_verify_batch_bytes(ctx):
+    cfg = (3, 0, 16, 8)
+    rng = np.random.default_rng(23)
+    n, blob_len = 12, 9000
+    blobs = rng.integers(0, 256, (n, blob_len), dtype=np.uint8)
+    seeds = [5 + i for i in range(n)]
+    _, proofs = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    proofs[4].c.inner_layers[0].hash_witness[1] ^= 1
+    proofs[9].proof_of_work ^= 1
+    pieces = [p.serialize() for p in proofs]
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(b) for b in pieces])
+    blob = np.frombuffer(b"".join(pieces), dtype=np.uint8)
+    got = ctx.verify_batch_bytes(blob, offs, seeds)
+    assert got == [0 if i in (4, 9) else 1 for i in range(n)]
+    assert got == ctx.verify_batch(proofs, seeds)
+    # truncated / garbage proofs are rejected, not crashed on
+    bad = blob.copy()
+    bad[int(offs[2]): int(offs[2]) + 4] = 0
+    got2 = ctx.verify_batch_bytes(bad, offs, seeds)
+    assert got2[2] == 0 and got2[0] == 1
