@@ -73,7 +73,7 @@ struct Plan {
   size_t o_in = 0, o_in2 = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
   size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
   size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
-  size_t o_best = 0, o_next = 0, o_unsolved = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
+  size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
          o_evals = 0;
   size_t total = 0;
 };
@@ -158,7 +158,6 @@ struct frieda_ctx {
   bool debug_keep = false;
   bool have_last = false;
   Plan last;
-  std::vector<uint64_t> last_nonces;
 
   int fail(cudaError_t e, const char *what, int line) {
     char buf[512];
@@ -306,7 +305,6 @@ void layout(Plan &pl, size_t B, bool stage_input) {
   if (pl.prove) {
     pl.o_best = bp.take(B * 8);
     pl.o_next = bp.take(B * 8);
-    pl.o_unsolved = bp.take(256);
     pl.o_totals = bp.take(256);
   }
   pl.total = bp.off;
@@ -611,7 +609,6 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
                        out_kind, ctx->stream));
     ctx->last = w;
     ctx->have_last = true;
-    ctx->last_nonces.clear();
   }
   if (!device_io) {
     int err_flag = 0;
@@ -836,7 +833,6 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     if (oom) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
     ctx->last = w;
     ctx->have_last = true;
-    ctx->last_nonces.assign(h_best.begin(), h_best.end());
   }
   return FRIEDA_OK;
 }

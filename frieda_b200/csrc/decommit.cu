@@ -63,17 +63,6 @@ cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits
   return cudaGetLastError();
 }
 
-__global__ void count_unsolved_kernel(const unsigned long long *best, size_t n, uint32_t *count) {
-  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < n && best[b] == ~0ull) atomicAdd(count, 1u);
-}
-cudaError_t launch_count_unsolved(cudaStream_t st, const unsigned long long *best, size_t n_blobs, uint32_t *count) {
-  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
-  if (e != cudaSuccess) return e;
-  count_unsolved_kernel<<<(unsigned)((n_blobs + 255) / 256), 256, 0, st>>>(best, n_blobs, count);
-  return cudaGetLastError();
-}
-
 // ---------------------------------------------------------------- queries
 // One thread per blob: mix_u64(nonce), then exactly n_queries draws of 4-byte chunks masked to
 // the domain, inserted into an ordered set (insertion sort + dedup).

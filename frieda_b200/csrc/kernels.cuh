@@ -108,7 +108,6 @@ cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs);
 // blob in increasing order from next[b] (zeroed here).
 cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t limit, uint32_t ctas_per_blob,
                          unsigned long long *best, unsigned long long *next, size_t n_blobs);
-cudaError_t launch_count_unsolved(cudaStream_t st, const unsigned long long *best, size_t n_blobs, uint32_t *count);
 // mix_u64(nonce) then Queries::generate: sorted unique positions per blob.
 cudaError_t launch_queries(cudaStream_t st, Channel *chan, const unsigned long long *nonce, uint32_t log_domain,
                            uint32_t n_queries, uint32_t *queries, uint32_t *n_unique, size_t n_blobs);
