@@ -126,8 +126,8 @@ struct frieda_ctx {
   // grow-only buffers of the proof path: gathered witnesses on the device, pinned readback on the host
   uint8_t *d_gather = nullptr;
   size_t d_gather_bytes = 0;
-  uint8_t *h_pinned = nullptr;
-  size_t h_pinned_bytes = 0;
+  uint8_t *h_pinned[2] = {nullptr, nullptr};  // double-buffered: wave i is assembled while wave i+1 computes
+  size_t h_pinned_bytes[2] = {0, 0};
   // per-kernel timing with CUDA events on the launching stream (bench.py's roofline)
   bool profiling = false;
   struct ProfRec {
@@ -632,18 +632,89 @@ int ensure_gather(frieda_ctx *ctx, size_t bytes) {
   ctx->d_gather_bytes = want;
   return FRIEDA_OK;
 }
-int ensure_pinned(frieda_ctx *ctx, size_t bytes) {
-  if (ctx->h_pinned_bytes >= bytes) return FRIEDA_OK;
-  if (ctx->h_pinned) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFreeHost(ctx->h_pinned);
-    ctx->h_pinned = nullptr;
-    ctx->h_pinned_bytes = 0;
+int ensure_pinned(frieda_ctx *ctx, int idx, size_t bytes) {
+  if (ctx->h_pinned_bytes[idx] >= bytes) return FRIEDA_OK;
+  if (ctx->h_pinned[idx]) {
+    cudaFreeHost(ctx->h_pinned[idx]);
+    ctx->h_pinned[idx] = nullptr;
+    ctx->h_pinned_bytes[idx] = 0;
   }
   size_t want = bytes + bytes / 4 + 4096;
-  CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pinned), want, cudaHostAllocDefault));
-  ctx->h_pinned_bytes = want;
+  CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pinned[idx]), want, cudaHostAllocDefault));
+  ctx->h_pinned_bytes[idx] = want;
   return FRIEDA_OK;
+}
+
+// Host copy of one proof wave's results; two of them alternate so that the Proof objects of wave i are
+// assembled on host threads while the GPU already works on wave i + 1.
+struct ProveHostBuf {
+  std::vector<uint8_t> roots;
+  std::vector<frieda_qm31> last, evals;
+  std::vector<uint32_t> counts, nuniq;
+  std::vector<unsigned long long> offsets, best;
+  const uint8_t *fri = nullptr, *hash = nullptr;  // into the pinned readback buffer
+};
+
+// Assembles the frieda_proof objects of blobs [b0, b0 + nb) (src/proof.rs:67-76).  Returns false on OOM.
+bool assemble_wave(const ProveHostBuf &hb, size_t b0, size_t nb, const Geom &g, uint32_t nq,
+                   const frieda_pcs_config *cfg, uint8_t *roots_out, frieda_proof **proofs_out) {
+  const uint32_t L = g.n_layers;
+  std::atomic<bool> oom{false};
+  auto assemble = [&](size_t b) {
+    frieda_proof *pr = (frieda_proof *)std::calloc(1, sizeof(frieda_proof));
+    if (!pr) {
+      oom = true;
+      return;
+    }
+    proofs_out[b0 + b] = pr;
+    pr->pcs_config = *cfg;
+    pr->log_size_bound = g.p;
+    pr->proof_of_work = hb.best[b];
+    pr->n_inner_layers = g.n_inner;
+    pr->inner_layers = (frieda_layer_proof *)std::calloc(g.n_inner ? g.n_inner : 1, sizeof(frieda_layer_proof));
+    pr->n_last_layer_poly = 1u << g.log_last;
+    pr->last_layer_poly = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) << g.log_last);
+    pr->n_evaluations = hb.nuniq[b];
+    pr->evaluations = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (hb.nuniq[b] ? hb.nuniq[b] : 1));
+    if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations) {
+      oom = true;
+      return;
+    }
+    std::memcpy(pr->last_layer_poly, &hb.last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
+    std::memcpy(pr->evaluations, &hb.evals[b * nq], sizeof(frieda_qm31) * hb.nuniq[b]);
+    for (uint32_t l = 0; l < L; l++) {
+      frieda_layer_proof *lp = l == 0 ? &pr->first_layer : &pr->inner_layers[l - 1];
+      size_t ci = (b * L + l) * 2;
+      std::memcpy(lp->commitment, &hb.roots[(b * L + l) * 32], 32);
+      lp->n_fri_witness = hb.counts[ci];
+      lp->n_hash_witness = hb.counts[ci + 1];
+      lp->n_column_witness = 0;
+      lp->fri_witness = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (lp->n_fri_witness ? lp->n_fri_witness : 1));
+      lp->hash_witness = (uint8_t *)std::malloc(32 * (size_t)(lp->n_hash_witness ? lp->n_hash_witness : 1));
+      lp->column_witness = (uint32_t *)std::malloc(4);
+      if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness) {
+        oom = true;
+        return;
+      }
+      std::memcpy(lp->fri_witness, hb.fri + hb.offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
+      std::memcpy(lp->hash_witness, hb.hash + hb.offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
+    }
+    if (roots_out) std::memcpy(roots_out + (b0 + b) * 32, &hb.roots[b * L * 32], 32);
+  };
+  // proofs are independent: a few host threads
+  unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()),
+                                           std::min<size_t>(8, (nb + 31) / 32));
+  if (nt <= 1) {
+    for (size_t b = 0; b < nb; b++) assemble(b);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        for (size_t b = t; b < nb; b += nt) assemble(b);
+      });
+    for (auto &x : th) x.join();
+  }
+  return !oom;
 }
 
 // ---- prove -------------------------------------------------------------------------------
@@ -674,13 +745,29 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   tr.mark("arena");
   const Geom &g = pl.g;
   const uint32_t L = g.n_layers;
-  std::vector<uint8_t> h_roots;
-  std::vector<frieda_qm31> h_last, h_evals;
-  std::vector<uint32_t> h_counts, h_nuniq;
-  std::vector<unsigned long long> h_offsets, h_best;
+  ProveHostBuf hbuf[2];
+  // background assembly of the previous wave; joined before its buffer is reused and on every exit path
+  struct Workers {
+    std::thread th[2];
+    bool active[2] = {false, false};
+    std::atomic<bool> failed{false};
+    void join(int i) {
+      if (active[i]) {
+        th[i].join();
+        active[i] = false;
+      }
+    }
+    ~Workers() {
+      join(0);
+      join(1);
+    }
+  } workers;
   CU(cudaMemsetAsync(at<int>(ctx, pl.o_err), 0, sizeof(int), ctx->stream));
-  for (size_t b0 = 0; b0 < n; b0 += B) {
+  size_t wave_index = 0;
+  for (size_t b0 = 0; b0 < n; b0 += B, wave_index++) {
     size_t nb = std::min(B, n - b0);
+    const int bi = (int)(wave_index & 1);
+    ProveHostBuf &hb = hbuf[bi];
     Plan w = pl;
     w.B = nb;
     const uint8_t *d_in;
@@ -734,7 +821,8 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
     const size_t fri_pad = align_up(fri_bytes, 256);
     if ((rc = ensure_gather(ctx, fri_pad + hash_bytes + 256))) return rc;
-    if ((rc = ensure_pinned(ctx, fri_pad + hash_bytes + 256))) return rc;
+    workers.join(bi);  // the wave that used this host buffer two iterations ago is assembled
+    if ((rc = ensure_pinned(ctx, bi, fri_pad + hash_bytes + 256))) return rc;
     uint8_t *d_gather = ctx->d_gather;
     dp.fri_out = reinterpret_cast<QM31 *>(d_gather);
     dp.hash_out = d_gather + fri_pad;
@@ -743,27 +831,28 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     ctx->prof_end();
     if (le != cudaSuccess) return ctx->fail(le, "launch_decommit_write", __LINE__);
     ctx->launches += 2;
-    h_roots.resize(nb * L * 32);
-    h_last.resize(nb << g.log_last);
-    h_evals.resize(nb * nq);
-    h_counts.resize(nb * L * 2);
-    h_offsets.resize(nb * L * 2);
-    h_nuniq.resize(nb);
-    h_best.resize(nb);
+    hb.roots.resize(nb * L * 32);
+    hb.last.resize(nb << g.log_last);
+    hb.evals.resize(nb * nq);
+    hb.counts.resize(nb * L * 2);
+    hb.offsets.resize(nb * L * 2);
+    hb.nuniq.resize(nb);
+    hb.best.resize(nb);
     int err_flag = 0;
     cudaError_t ce = cudaSuccess;
     auto cp = [&](void *dst, const void *src, size_t bytes) {
       if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     };
-    cp(h_roots.data(), at<uint8_t>(ctx, w.o_roots), h_roots.size());
-    cp(h_last.data(), at<QM31>(ctx, w.o_last), h_last.size() * sizeof(frieda_qm31));
-    cp(h_evals.data(), dp.evals_out, h_evals.size() * sizeof(frieda_qm31));
-    cp(h_counts.data(), dp.counts, h_counts.size() * 4);
-    cp(h_offsets.data(), dp.offsets, h_offsets.size() * 8);
-    cp(h_nuniq.data(), nuniq, nb * 4);
-    cp(h_best.data(), best, nb * 8);
-    cp(ctx->h_pinned, d_gather, fri_pad + hash_bytes);  // witnesses: one copy into pinned memory
-    const uint8_t *h_fri = ctx->h_pinned, *h_hash = ctx->h_pinned + fri_pad;
+    cp(hb.roots.data(), at<uint8_t>(ctx, w.o_roots), hb.roots.size());
+    cp(hb.last.data(), at<QM31>(ctx, w.o_last), hb.last.size() * sizeof(frieda_qm31));
+    cp(hb.evals.data(), dp.evals_out, hb.evals.size() * sizeof(frieda_qm31));
+    cp(hb.counts.data(), dp.counts, hb.counts.size() * 4);
+    cp(hb.offsets.data(), dp.offsets, hb.offsets.size() * 8);
+    cp(hb.nuniq.data(), nuniq, nb * 4);
+    cp(hb.best.data(), best, nb * 8);
+    cp(ctx->h_pinned[bi], d_gather, fri_pad + hash_bytes);  // witnesses: one copy into pinned memory
+    hb.fri = ctx->h_pinned[bi];
+    hb.hash = ctx->h_pinned[bi] + fri_pad;
     cp(&err_flag, at<int>(ctx, w.o_err), sizeof(int));
     tr.mark("write launch + readback enqueue");
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
@@ -771,69 +860,23 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
     if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
     for (size_t b = 0; b < nb; b++)
-      if (h_best[b] == ~0ull) return ctx->fail_arg("proof of work search exhausted");
-    // assemble Proof objects (src/proof.rs:67-76)
-    std::atomic<bool> oom{false};
-    auto assemble = [&](size_t b) {
-      frieda_proof *pr = (frieda_proof *)std::calloc(1, sizeof(frieda_proof));
-      if (!pr) {
-        oom = true;
-        return;
-      }
-      proofs_out[b0 + b] = pr;
-      pr->pcs_config = *cfg;
-      pr->log_size_bound = g.p;
-      pr->proof_of_work = h_best[b];
-      pr->n_inner_layers = g.n_inner;
-      pr->inner_layers = (frieda_layer_proof *)std::calloc(g.n_inner ? g.n_inner : 1, sizeof(frieda_layer_proof));
-      pr->n_last_layer_poly = 1u << g.log_last;
-      pr->last_layer_poly = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) << g.log_last);
-      pr->n_evaluations = h_nuniq[b];
-      pr->evaluations = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (h_nuniq[b] ? h_nuniq[b] : 1));
-      if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations) {
-        oom = true;
-        return;
-      }
-      std::memcpy(pr->last_layer_poly, &h_last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
-      std::memcpy(pr->evaluations, &h_evals[b * nq], sizeof(frieda_qm31) * h_nuniq[b]);
-      for (uint32_t l = 0; l < L; l++) {
-        frieda_layer_proof *lp = l == 0 ? &pr->first_layer : &pr->inner_layers[l - 1];
-        size_t ci = (b * L + l) * 2;
-        std::memcpy(lp->commitment, &h_roots[(b * L + l) * 32], 32);
-        lp->n_fri_witness = h_counts[ci];
-        lp->n_hash_witness = h_counts[ci + 1];
-        lp->n_column_witness = 0;
-        lp->fri_witness = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (lp->n_fri_witness ? lp->n_fri_witness : 1));
-        lp->hash_witness = (uint8_t *)std::malloc(32 * (size_t)(lp->n_hash_witness ? lp->n_hash_witness : 1));
-        lp->column_witness = (uint32_t *)std::malloc(4);
-        if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness) {
-          oom = true;
-          return;
-        }
-        std::memcpy(lp->fri_witness, h_fri + h_offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
-        std::memcpy(lp->hash_witness, h_hash + h_offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
-      }
-      if (roots_out) std::memcpy(roots_out + (b0 + b) * 32, &h_roots[b * L * 32], 32);
-    };
-    {
-      // proofs are independent: assemble them on a few host threads
-      unsigned nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<size_t>(8, (nb + 31) / 32));
-      if (nt <= 1) {
-        for (size_t b = 0; b < nb; b++) assemble(b);
-      } else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++)
-          th.emplace_back([&, t]() {
-            for (size_t b = t; b < nb; b += nt) assemble(b);
-          });
-        for (auto &x : th) x.join();
-      }
+      if (hb.best[b] == ~0ull) return ctx->fail_arg("proof of work search exhausted");
+    // assemble this wave's Proof objects in the background while the next wave computes
+    if (b0 + B < n) {
+      workers.th[bi] = std::thread([&workers, &hb, b0, nb, &g, nq, cfg, roots_out, proofs_out]() {
+        if (!assemble_wave(hb, b0, nb, g, nq, cfg, roots_out, proofs_out)) workers.failed = true;
+      });
+      workers.active[bi] = true;
+    } else if (!assemble_wave(hb, b0, nb, g, nq, cfg, roots_out, proofs_out)) {
+      workers.failed = true;
     }
     tr.mark("assemble");
-    if (oom) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
     ctx->last = w;
     ctx->have_last = true;
   }
+  workers.join(0);
+  workers.join(1);
+  if (workers.failed) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
   return FRIEDA_OK;
 }
 
@@ -894,7 +937,8 @@ void frieda_ctx_destroy(frieda_ctx *ctx) {
   cudaFree(ctx->arena);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_gather);
-  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < 2; i++)
+    if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
   for (auto &r : ctx->prof_recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);

@@ -694,3 +694,25 @@ def test_verify_batch_bytes(ctx):
     bad[int(offs[2]): int(offs[2]) + 4] = 0
     got2 = ctx.verify_batch_bytes(bad, offs, seeds)
     assert got2[2] == 0 and got2[0] == 1
+
+
+# ------------------------------------------------------------------ error paths through the C ABI
+def test_error_paths_fail_loudly(ctx):
+    from frieda_b200 import api
+    blobs = np.zeros((2, 1000), dtype=np.uint8)
+    cases = [
+        (lambda: ctx.prove_batch(blobs, None, F.PcsConfig(4, 0, 0, 4)), api.ERR_PANIC),       # n_queries 0 never returns
+        (lambda: ctx.prove_batch(blobs, None, F.PcsConfig(4, 0, 5000, 4)), api.ERR_ARG),      # n_queries > 4096
+        (lambda: ctx.prove_batch(blobs, None, F.PcsConfig(4, 0, 8, 41)), api.ERR_ARG),        # pow_bits > 40
+        (lambda: ctx.fri_commit_batch(blobs, None, F.PcsConfig(8, 2, 8, 4)), api.ERR_ARG),    # last layer > 2^9
+        (lambda: ctx.fri_commit_batch(blobs, None, F.PcsConfig(4, 9, 8, 4)), api.ERR_PANIC),  # poly too small
+        (lambda: ctx.commit_batch_ptr(blobs.ctypes.data, 1000, 10, 2, 4, blobs.ctypes.data, device=False),
+         api.ERR_ARG),                                                                          # stride < len
+        (lambda: ctx.commit(bytes(10), 40), api.ERR_ARG),                                      # domain > 2^28
+    ]
+    for fn, code in cases:
+        with pytest.raises(F.FriedaError) as ei:
+            fn()
+        assert ei.value.code == code, (ei.value.code, code, str(ei.value))
+    # the context stays usable after errors
+    assert ctx.commit(b"abc", 3) == O.commit(b"abc", 3)
