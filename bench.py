@@ -129,8 +129,9 @@ def synth_blobs(n, rank_offset=0):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_sample(n_threads: int, blobs_per_thread: int):
-    """Times the CPU oracle (FRI commit phase per blob) on n_threads host threads."""
+def cpu_sample(n_threads: int, blobs_per_thread: int, results=None):
+    """Times the CPU oracle (FRI commit phase per blob) on n_threads host threads.  Thread i works on
+    synthetic blob i; `results[i]` receives its layer roots (the checker side of the parity spot check)."""
     import numpy as np
     from oracle import oracle as O
     O.lib()
@@ -141,7 +142,9 @@ def cpu_sample(n_threads: int, blobs_per_thread: int):
     def work(i):
         try:
             for _ in range(blobs_per_thread):
-                O.fri_commit(data[i], None, cfg)
+                roots, _ = O.fri_commit(data[i], None, cfg)
+            if results is not None:
+                results[i] = roots
         except Exception as e:  # pragma: no cover
             errs.append(e)
 
@@ -371,7 +374,14 @@ def main():
         n_threads = max(1, min(cores, 64))
         v1, t1 = cpu_sample(1, 1)
         per_thread = max(1, min(8, int(round(12.0 / max(t1, 1e-3)))))
-        v, dt = cpu_sample(n_threads, per_thread)
+        oracle_roots = {}
+        v, dt = cpu_sample(n_threads, per_thread, oracle_roots)
+        # the baseline run doubles as a parity check: the oracle's layer roots of blobs 0..n_threads-1
+        # against what the timed GPU path produced for the same blobs
+        gpu_roots = h_roots.numpy()
+        same = all(b"".join(oracle_roots[i]) == gpu_roots[i].tobytes() for i in oracle_roots)
+        line["parity_vs_oracle"] = {"blobs_checked": len(oracle_roots), "layer_roots_per_blob": L, "all_equal": same}
+        assert same, "GPU layer roots differ from the oracle"
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": n_threads, "kind": "port",
                                 "sample": f"{n_threads * per_thread} blobs ({per_thread} per thread) in {dt:.1f} s; "
                                           f"1 thread: {v1:.3f} blobs/s",
