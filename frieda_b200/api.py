@@ -93,7 +93,7 @@ EXPORTS = [
     "frieda_verify_core_host", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device",
-    "frieda_merkle_combine", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
+    "frieda_merkle_combine", "frieda_decode_block", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
 
@@ -145,6 +145,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_commit_split_local": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_commit_split_local_device": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_merkle_combine": (C.c_int, [vp, vp, C.c_uint32, u8p]),
+        "frieda_decode_block": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, vp]),
         "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
         "frieda_pass_lde": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp]),
         "frieda_pass_merkle": (C.c_int, [vp, vp, C.c_uint32, sz, vp, vp]),
@@ -444,6 +445,16 @@ class Context:
         out = (C.c_uint8 * 32)()
         self._check(self._L.frieda_merkle_combine(self._h, subroots_dev_ptr, world, out))
         return bytes(out)
+
+    # -- erasure recovery ------------------------------------------------------------
+    def decode_block(self, block_evals: np.ndarray, length: int, log_blowup_factor: int, block: int) -> bytes:
+        """Recovers the `length` original bytes from ONE coset block of the evaluation:
+        block_evals = (4, 2^poly_log) uint32, the entries [block 2^p, (block+1) 2^p) of each column."""
+        ev = np.ascontiguousarray(block_evals, dtype=np.uint32)
+        out = np.zeros(max(length, 1), dtype=np.uint8)
+        self._check(self._L.frieda_decode_block(self._h, ev.ctypes.data, length, log_blowup_factor, block,
+                                                out.ctypes.data))
+        return out[:length].tobytes()
 
     # -- standalone passes / introspection ------------------------------------------
     def twiddles(self, k: int):

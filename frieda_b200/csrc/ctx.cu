@@ -1153,6 +1153,40 @@ int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t w
   return FRIEDA_OK;
 }
 
+// ---- erasure recovery ----------------------------------------------------------
+// block_evals (host): 4 columns x 2^poly_log evaluations = indices [block 2^p, (block+1) 2^p) of each column
+// of the committed evaluation (bit-reversed domain order).  Writes the original `len` bytes to data_out.
+int frieda_decode_block(frieda_ctx *ctx, const uint32_t *block_evals, size_t len, uint32_t log_blowup, uint32_t block,
+                        uint8_t *data_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!block_evals || (!data_out && len)) return ctx->fail_arg("null pointer");
+  CU(cudaSetDevice(ctx->device));
+  Geom g;
+  int rc = make_geom(ctx, len, log_blowup, g);
+  if (rc) return rc;
+  if (g.D < 3) return ctx->fail_arg("domain too small to decode");
+  if (g.p > 15) return ctx->fail_arg("decode of polynomials above 2^15 coefficients per column is not supported");
+  if (block >= (1u << log_blowup)) return ctx->fail_arg("block index out of range");
+  if ((rc = ensure_twiddles(ctx, g.D - 1))) return rc;
+  Bump bp;
+  const size_t n_coef = (size_t)4 << g.p;
+  size_t o_ev = bp.take(n_coef * 4), o_coef = bp.take(n_coef * 4), o_out = bp.take(len ? len : 1), o_flag = bp.take(256);
+  if ((rc = ensure_arena(ctx, bp.off))) return rc;
+  ctx->have_last = false;
+  CU(cudaMemcpyAsync(at<uint32_t>(ctx, o_ev), block_evals, n_coef * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(at<int>(ctx, o_flag), 0, sizeof(int), ctx->stream));
+  KL("decode_block", launch_decode_block(ctx->stream, at<uint32_t>(ctx, o_ev), at<uint32_t>(ctx, o_coef), g.p, g.beta,
+                                         block, table(ctx), len, g.n_felts, at<uint8_t>(ctx, o_out),
+                                         at<int>(ctx, o_flag)),
+     2);
+  int flag = 0;
+  if (len) CU(cudaMemcpyAsync(data_out, at<uint8_t>(ctx, o_out), len, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&flag, at<int>(ctx, o_flag), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (flag) return ctx->fail_arg("the evaluations are not an encoding of `len` bytes");
+  return FRIEDA_OK;
+}
+
 // ---- standalone passes ------------------------------------------------------------------------
 int frieda_pass_pack(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride, size_t n,
                      uint32_t *d_coeffs) {

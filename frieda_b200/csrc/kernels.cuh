@@ -66,6 +66,10 @@ struct LdeRange {
 cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t poly_log, uint32_t log_blowup,
                        size_t n_blobs, uint32_t n_felts, const TwiddleTable &tt, CPoint half_initial,
                        const LdeRange *range = nullptr);
+// Erasure recovery: one coset block (4 columns x 2^p evaluations, block index hb) -> coefficients -> bytes.
+cudaError_t launch_decode_block(cudaStream_t st, const uint32_t *block_evals, uint32_t *coef, uint32_t p,
+                                uint32_t beta, uint32_t hb, const TwiddleTable &tt, size_t len, uint32_t n_felts,
+                                uint8_t *out, int *flag);
 cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomParams &p, size_t n_blobs);
 // One CTA per blob: reduce 2^top_log nodes at tree level top_log to the root; optionally
 // mix_root + draw the folding alpha on the blob's channel.

@@ -412,6 +412,104 @@ __global__ void __launch_bounds__(256) lde_strided_r16_kernel(const uint32_t *__
   }
 }
 
+// ---------------------------------------------------------------- decode (erasure recovery)
+// Any one of the 2^log_blowup coset blocks of an evaluation column determines the polynomial: the
+// block is the 2^p-point FFT of the coefficients with block-specific twiddles, so running the
+// layers backwards (circle layer first, then the line layers with growing stride) with the inverse
+// twiddles and scaling by 2^-p recovers the coefficients.  ibutterfly: (x, y) -> (x + y, (x - y) / t).
+// This is the decode side of the Reed-Solomon code the commit path encodes (the
+// reference's README describes sampling/recovery but its code has no counterpart).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) lde_block_inverse_kernel(const uint32_t *__restrict__ block_evals,
+                                                                    uint32_t *__restrict__ coef, uint32_t p,
+                                                                    uint32_t beta, uint32_t hb, uint32_t inv_n,
+                                                                    TwiddleTable tt) {
+  extern __shared__ uint32_t smi[];
+  const uint32_t col = blockIdx.x;
+  const uint32_t n4 = 1u << p;
+  const uint32_t D = p + beta, K = D - 1;
+  const uint32_t *src = block_evals + (size_t)col * n4;
+  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) smi[i] = src[i];
+  __syncthreads();
+  const uint32_t half = n4 >> 1;
+  if (p >= 1) {
+    // circle layer (pairs of neighbours), inverse twiddles [1/y, -1/y, -1/x, 1/x]
+    const uint32_t *itw0 = tt.iblk(1u << (K - 1));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t h = (hb << (p - 1)) | bf;
+      uint32_t q = h >> 2, e = h & 3;
+      uint32_t ix = __ldg(itw0 + 2 * q), iy = __ldg(itw0 + 2 * q + 1);
+      uint32_t it = e == 0 ? iy : e == 1 ? m31_neg(iy) : e == 2 ? m31_neg(ix) : ix;
+      uint32_t x = smi[2 * bf], y = smi[2 * bf + 1];
+      smi[2 * bf] = m31_add(x, y);
+      smi[2 * bf + 1] = m31_mul(m31_sub(x, y), it);
+    }
+    __syncthreads();
+  }
+  for (uint32_t i = 1; i < p; i++) {
+    const uint32_t *itw = tt.iblk(1u << (K - i)) + ((size_t)hb << (p - i - 1));
+    for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
+      uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
+      uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
+      uint32_t it = __ldg(itw + hi);
+      uint32_t x = smi[a], y = smi[b];
+      smi[a] = m31_add(x, y);
+      smi[b] = m31_mul(m31_sub(x, y), it);
+    }
+    __syncthreads();
+  }
+  uint32_t *dst = coef + (size_t)col * n4;
+  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) dst[i] = m31_mul(smi[i], inv_n);
+}
+
+// Inverse of pack_kernel: 30-bit limbs back to bytes.  flag[0] is set when the coefficients are not
+// a packing of `len` bytes (a limb >= 2^30, or non-zero padding), i.e. the block was not a codeword.
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict__ coef, uint32_t n_coef,
+                                                      uint32_t n_felts, size_t len, uint8_t *__restrict__ out,
+                                                      int *flag) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = gid; i < len; i += stride) {
+    const uint64_t bit = 8ull * i;
+    const uint32_t k = (uint32_t)(bit / 30), off = (uint32_t)(bit % 30);
+    uint64_t v = coef[k];
+    if (off > 22 && k + 1 < n_coef) v |= (uint64_t)coef[k + 1] << 30;
+    out[i] = (uint8_t)(v >> off);
+  }
+  for (size_t k = gid; k < n_coef; k += stride) {
+    uint32_t c = coef[k];
+    bool bad = c >= (1u << 30) || (k >= n_felts && c != 0);
+    if (k + 1 == n_felts) {
+      // the last limb only carries the remaining bits
+      uint32_t used = (uint32_t)(8ull * len - 30ull * k);
+      if (used < 30 && (c >> used)) bad = true;
+    }
+    if (bad) atomicExch(flag, 1);
+  }
+}
+
+cudaError_t launch_decode_block(cudaStream_t st, const uint32_t *block_evals, uint32_t *coef, uint32_t p,
+                                uint32_t beta, uint32_t hb, const TwiddleTable &tt, size_t len, uint32_t n_felts,
+                                uint8_t *out, int *flag) {
+  if (p > 15 || p + beta < 3) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(lde_block_inverse_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
+    attr = true;
+  }
+  const uint32_t inv_n = m31_inv(1u << p);
+  lde_block_inverse_kernel<1024><<<4, 1024, (size_t)4 << p, st>>>(block_evals, coef, p, beta, hb, inv_n, tt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const uint32_t n_coef = 4u << p;
+  size_t work = len > n_coef ? len : n_coef;
+  unsigned bx = (unsigned)((work + 255) / 256);
+  if (bx > 4096) bx = 4096;
+  if (bx == 0) bx = 1;
+  unpack_kernel<<<bx, 256, 0, st>>>(coef, n_coef, n_felts, len, out, flag);
+  return cudaGetLastError();
+}
+
 constexpr uint32_t LDE_SMEM_LOG_MAX = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
 
 cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t p, uint32_t beta,

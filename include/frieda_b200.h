@@ -172,6 +172,14 @@ int frieda_commit_split_local_device(frieda_ctx *ctx, const uint8_t *d_data, siz
  * (d_subroots = world * 32 bytes of device memory, rank order) into root_out (host). */
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]);
 
+/* ---- erasure recovery (the reference's README promises sampling/recovery, its code has none) --
+ * Any ONE of the 2^log_blowup coset blocks of the committed evaluation determines the data.  block_evals (host):
+ * 4 columns x 2^poly_log u32 = entries [block * 2^poly_log, (block + 1) * 2^poly_log) of each evaluation column
+ * (bit-reversed domain order, as produced by the commit path).  Writes the original `len` bytes to data_out;
+ * FRIEDA_ERR_ARG if the block is not an encoding of `len` bytes.  poly_log <= 15 in this build. */
+int frieda_decode_block(frieda_ctx *ctx, const uint32_t *block_evals, size_t len, uint32_t log_blowup, uint32_t block,
+                        uint8_t *data_out);
+
 /* ---- standalone passes (bench.py's per-pass roofline; tests).  Device pointers. --------
  * LDE: d_coeffs = n * 4 * 2^poly_log u32 -> d_evals = n * 4 * 2^(poly_log+log_blowup) u32. */
 int frieda_pass_pack(frieda_ctx *ctx, const uint8_t *d_blobs, size_t blob_len, size_t blob_stride, size_t n,

@@ -716,3 +716,32 @@ def test_error_paths_fail_loudly(ctx):
         assert ei.value.code == code, (ei.value.code, code, str(ei.value))
     # the context stays usable after errors
     assert ctx.commit(b"abc", 3) == O.commit(b"abc", 3)
+
+
+# ------------------------------------------------------------------ encode -> erase -> decode
+@pytest.mark.parametrize("n_bytes,blow", [(58, 4), (1000, 2), (4097, 3), (65536, 1), (131072, 4), (262146, 4)])
+def test_encode_erase_decode_round_trip(ctx, torch_mod, blob_bytes, n_bytes, blow):
+    # commit-path evaluations -> keep ONE of the 2^blowup coset blocks (erase the rest) -> recover the bytes
+    torch = torch_mod
+    data = blob_bytes if n_bytes == 262146 else O.splitmix64_bytes(0x4652494544410000 + n_bytes, n_bytes)
+    p = O.poly_log(len(data))
+    D = p + blow
+    n_felts = (len(data) * 8 + 29) // 30
+    coef = np.zeros(4 << p, dtype=np.uint32)
+    coef[:n_felts] = O.bytes_to_felts(data)
+    d_coef = torch.from_numpy(coef.view(np.int32)).cuda()
+    d_eval = torch.zeros(4 << D, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.pass_lde(d_coef.data_ptr(), p, blow, 1, n_felts, d_eval.data_ptr())
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    ev = d_eval.cpu().numpy().view(np.uint32).reshape(4, 1 << D)
+    for block in sorted({0, 1, (1 << blow) - 1, (1 << blow) // 2}):
+        piece = ev[:, block << p: (block + 1) << p]
+        assert ctx.decode_block(piece, len(data), blow, block) == data, (n_bytes, blow, block)
+    # a corrupted block is not an encoding of `len` bytes (or decodes to different data)
+    bad = ev[:, : 1 << p].copy()
+    bad[0, 0] ^= 1
+    try:
+        assert ctx.decode_block(bad, len(data), blow, 0) != data
+    except F.FriedaError as e:
+        assert e.code == -4
