@@ -77,14 +77,48 @@ inline uint32_t fr_add(uint32_t x, uint32_t y, uint32_t) { return x + y; }
     FR_G(v3, v4, v9, v14, s14, s15);                                                    \
   } while (0)
 
+// G with zero message words on compile-time constants (for the constant part of a leaf hash).
+struct GConst {
+  uint32_t a, b, c, d;
+};
+constexpr uint32_t c_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+constexpr GConst g_zero_msg(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  a = a + b;
+  d = c_rotr(d ^ a, 16);
+  c = c + d;
+  b = c_rotr(b ^ c, 12);
+  a = a + b;
+  d = c_rotr(d ^ a, 8);
+  c = c + d;
+  b = c_rotr(b ^ c, 7);
+  return {a, b, c, d};
+}
+
 // h <- compress(h, m, t0, t1, f0, f1).  Fully unrolled, state in registers.
-template <uint32_t MASK>
+// ZERO_LEAF: the caller guarantees h == 0, t = f = 0 and m[4..15] == 0 (a Merkle leaf): columns 2 and 3 of
+// round 0's first half then see only constants and are folded at compile time (the opaque IMAD adds would
+// otherwise hide that from the compiler).
+template <uint32_t MASK, bool ZERO_LEAF = false>
 FR_HD void blake2s_compress_t(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
                               uint32_t f1, uint32_t one) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   uint32_t v8 = FR_B2S_IV0, v9 = FR_B2S_IV1, v10 = FR_B2S_IV2, v11 = FR_B2S_IV3;
   uint32_t v12 = FR_B2S_IV4 ^ t0, v13 = FR_B2S_IV5 ^ t1, v14 = FR_B2S_IV6 ^ f0, v15 = FR_B2S_IV7 ^ f1;
-  FR_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  if (ZERO_LEAF) {
+    static_assert(!ZERO_LEAF || MASK == 0x000Fu, "ZERO_LEAF is the 4-word leaf message");
+    FR_G(v0, v4, v8, v12, 0, 1);
+    FR_G(v1, v5, v9, v13, 2, 3);
+    constexpr GConst c2 = g_zero_msg(0u, 0u, FR_B2S_IV2, FR_B2S_IV6);
+    constexpr GConst c3 = g_zero_msg(0u, 0u, FR_B2S_IV3, FR_B2S_IV7);
+    v2 = c2.a; v6 = c2.b; v10 = c2.c; v14 = c2.d;
+    v3 = c3.a; v7 = c3.b; v11 = c3.c; v15 = c3.d;
+    FR_G(v0, v5, v10, v15, 8, 9);
+    FR_G(v1, v6, v11, v12, 10, 11);
+    FR_G(v2, v7, v8, v13, 12, 13);
+    FR_G(v3, v4, v9, v14, 14, 15);
+  } else {
+    FR_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  }
   FR_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
   FR_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
   FR_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
@@ -114,7 +148,7 @@ FR_HD void merkle_hash_leaf(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
   uint32_t m[16] = {c0, c1, c2, c3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 8; i++) out[i] = 0;
-  blake2s_compress_t<0x000Fu>(out, m, 0, 0, 0, 0, one);
+  blake2s_compress_t<0x000Fu, true>(out, m, 0, 0, 0, 0, one);
 }
 // Merkle inner node: hash_node(Some((left, right)), []); m = left || right.
 FR_HD void merkle_hash_node(const uint32_t m[16], uint32_t out[8], uint32_t one = 1u) {
