@@ -116,7 +116,7 @@ struct frieda_ctx {
   // twiddle cache
   bool tw_valid = false;
   uint32_t tw_K = 0;
-  uint32_t *d_tw = nullptr, *d_itw = nullptr;
+  uint32_t *d_tw = nullptr, *d_itw = nullptr, *d_tw2 = nullptr;
   GenPowers gp;
   // workspace arena
   uint8_t *arena = nullptr;
@@ -227,19 +227,21 @@ int ensure_twiddles(frieda_ctx *ctx, uint32_t K) {
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_tw);
     cudaFree(ctx->d_itw);
-    ctx->d_tw = ctx->d_itw = nullptr;
+    cudaFree(ctx->d_tw2);
+    ctx->d_tw = ctx->d_itw = ctx->d_tw2 = nullptr;
     ctx->tw_valid = false;
   }
   size_t bytes = sizeof(uint32_t) << K;
   CU(cudaMalloc(&ctx->d_tw, bytes));
   CU(cudaMalloc(&ctx->d_itw, bytes));
-  KL("twiddles", launch_twiddles(ctx->stream, ctx->gp, K, ctx->d_tw, ctx->d_itw), 1);
+  CU(cudaMalloc(&ctx->d_tw2, bytes));
+  KL("twiddles", launch_twiddles(ctx->stream, ctx->gp, K, ctx->d_tw, ctx->d_itw, ctx->d_tw2), 1);
   ctx->tw_K = K;
   ctx->tw_valid = true;
   return FRIEDA_OK;
 }
 
-TwiddleTable table(const frieda_ctx *ctx) { return TwiddleTable{ctx->d_tw, ctx->d_itw, ctx->tw_K}; }
+TwiddleTable table(const frieda_ctx *ctx) { return TwiddleTable{ctx->d_tw, ctx->d_itw, ctx->d_tw2, ctx->tw_K}; }
 
 int ensure_arena(frieda_ctx *ctx, size_t bytes) {
   if (ctx->arena_bytes >= bytes) return FRIEDA_OK;
@@ -934,6 +936,7 @@ void frieda_ctx_destroy(frieda_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_tw);
   cudaFree(ctx->d_itw);
+  cudaFree(ctx->d_tw2);
   cudaFree(ctx->arena);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_gather);

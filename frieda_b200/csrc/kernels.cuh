@@ -24,8 +24,10 @@ namespace frieda {
 struct TwiddleTable {
   const uint32_t *tw;   // forward, 2^K
   const uint32_t *itw;  // element-wise inverses
+  const uint32_t *tw2;  // forward, doubled (2t < 2^32): the operand form of m31_mul_t2
   uint32_t K;
   FR_HD const uint32_t *blk(uint32_t s) const { return tw + (((size_t)1 << K) - 2 * (size_t)s); }
+  FR_HD const uint32_t *blk2(uint32_t s) const { return tw2 + (((size_t)1 << K) - 2 * (size_t)s); }
   FR_HD const uint32_t *iblk(uint32_t s) const { return itw + (((size_t)1 << K) - 2 * (size_t)s); }
 };
 
@@ -55,7 +57,8 @@ struct MerkleBottomParams {
 
 cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
                         uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
-cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw);
+cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw,
+                            uint32_t *tw2);
 // Owned slice of the evaluation domain (bit-reversed order): [lo, lo + 2^log); lo is a
 // multiple of 2^log.  The evaluation buffer then holds 4 x 2^log words per blob.
 struct LdeRange {

@@ -11,6 +11,9 @@
 // hb using the twiddles whose index has hb as its high bits.  Each (blob, column, block) is one
 // CTA working in shared memory; HBM sees the coefficients once (L2 for re-reads) and the
 // evaluations once.
+#include <cstdlib>
+#include <utility>
+
 #include "kernels.cuh"
 
 namespace frieda {
@@ -72,7 +75,8 @@ __device__ __forceinline__ CPoint point_from_index(const GenPowers &gp, uint32_t
 }
 
 __global__ void __launch_bounds__(256) twiddle_kernel(const __grid_constant__ GenPowers gp, uint32_t K,
-                                                       uint32_t *__restrict__ tw, uint32_t *__restrict__ itw) {
+                                                       uint32_t *__restrict__ tw, uint32_t *__restrict__ itw,
+                                                       uint32_t *__restrict__ tw2) {
   size_t len = (size_t)1 << K;
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= len) return;
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(256) twiddle_kernel(const __grid_constant__ Ge
   if (rem == 1) {
     tw[g] = 1;
     itw[g] = 1;
+    tw2[g] = 2;
     return;
   }
   // the block of length s occupies [len - 2s, len - s): s = largest power of two < rem
@@ -90,12 +95,14 @@ __global__ void __launch_bounds__(256) twiddle_kernel(const __grid_constant__ Ge
   uint32_t x = point_from_index(gp, idx).x;
   tw[g] = x;
   itw[g] = m31_inv(x);
+  tw2[g] = x + x;
 }
 
-cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw) {
+cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw,
+                            uint32_t *tw2) {
   size_t len = (size_t)1 << K;
   unsigned blocks = (unsigned)((len + 255) / 256);
-  twiddle_kernel<<<blocks, 256, 0, st>>>(gp, K, tw, itw);
+  twiddle_kernel<<<blocks, 256, 0, st>>>(gp, K, tw, itw, tw2);
   return cudaGetLastError();
 }
 
@@ -314,6 +321,197 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *coef
 #pragma unroll 1
   for (uint32_t g = threadIdx.x; g < (n4 >> R_LAST); g += THREADS)
     last_pass<R_LAST>(src, S::NP != 0, out, g, tt, K, p, hb, w_lo, w_n, full);
+}
+
+// ---------------------------------------------------------------- LDE, warp-tiled (2^10 .. 2^15-point blocks)
+// Same (block hb, column, blob) decomposition as lde_block_kernel, scheduled so that only ONE
+// CTA-wide barrier remains:
+//   A  layers P-1 .. 10 (radix 2^(P-10), twiddles uniform over the CTA, held in registers):
+//      thread-task = one of the 1024 low index positions, coefficients straight from HBM/L2;
+//   -- __syncthreads --
+//   the block is now 2^(P-10) independent 1024-point sub-FFTs; each is done by ONE warp:
+//   B  layers 9 .. 5, lane = index bits 4..0, registers = bits 9..5 (twiddles uniform over the
+//      warp, fetched as 128-bit loads);
+//   -- __syncwarp (transpose through the warp's own 32 rows of 36 words) --
+//   C  layers 4 .. 1 and the circle layer on 32 consecutive points per lane (128-bit shared loads,
+//      per-lane twiddles as 128-bit loads, results to HBM as 256-bit stores).
+// Warps drift apart after the barrier, so the load/store phases of one warp overlap the arithmetic
+// of the others.  Rows of 32 words are padded to 36: lane-consecutive scalar accesses and 128-bit
+// row accesses are both bank-conflict free.  Twiddles come pre-doubled (TwiddleTable::tw2); a
+// butterfly with twiddle -t is the butterfly with t and its outputs swapped, so the circle layer
+// [y, -y, -x, x] needs no negation.
+__device__ __forceinline__ void bfly_t2_swapped(uint32_t &a, uint32_t &b, uint32_t t2) {
+  uint32_t tmp = m31_mul_t2(b, t2), va = a;
+  a = m31_sub(va, tmp);
+  b = m31_add(va, tmp);
+}
+
+template <int N>
+__device__ __forceinline__ void load_tw_vec(const uint32_t *p, uint32_t (&t)[N]) {
+  if constexpr (N == 1) {
+    t[0] = __ldg(p);
+  } else if constexpr (N == 2) {
+    uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    t[0] = q.x; t[1] = q.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < N / 4; j++) {
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + j);
+      t[4 * j] = q.x; t[4 * j + 1] = q.y; t[4 * j + 2] = q.z; t[4 * j + 3] = q.w;
+    }
+  }
+}
+
+// stage S of a radix-N register pass: 2^S groups of N >> S values, one (doubled) twiddle per group
+template <int N, int S>
+__device__ __forceinline__ void reg_stage(uint32_t (&v)[N], const uint32_t *t2) {
+  constexpr int half = N >> (S + 1);
+#pragma unroll
+  for (int q = 0; q < (1 << S); q++)
+#pragma unroll
+    for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2[q]);
+}
+
+// stages S .. NST-1 with all twiddles in one register array (stage s at t[2^s - 1 ..])
+template <int N, int NST, int S = 0>
+__device__ __forceinline__ void reg_stages_held(uint32_t (&v)[N], const uint32_t *t) {
+  if constexpr (S < NST) {
+    reg_stage<N, S>(v, t + ((1 << S) - 1));
+    reg_stages_held<N, NST, S + 1>(v, t);
+  }
+}
+
+// stages S .. NST-1 for line layers top, top-1, ..; row(i) = doubled-twiddle row of layer i offset
+// to element 0 of this group (global index >> (i+1)); stage s reads 2^s consecutive words there.
+template <int N, int NST, int S = 0, typename RowFn>
+__device__ __forceinline__ void reg_stages_vec(uint32_t (&v)[N], int top, RowFn row) {
+  if constexpr (S < NST) {
+    uint32_t t[1 << S];
+    load_tw_vec<(1 << S)>(row(top - S), t);
+    reg_stage<N, S>(v, t);
+    reg_stages_vec<N, NST, S + 1>(v, top, row);
+  }
+}
+
+constexpr int LDE_ROW = 36;            // padded row of 32 words
+constexpr int LDE_SUB = 32 * LDE_ROW;  // one 1024-point sub-FFT in shared memory
+
+template <int P, int THREADS, bool INPLACE>
+__global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef, uint32_t *eval, uint32_t beta,
+                                                           uint32_t n_felts, TwiddleTable tt, LdeRange rg,
+                                                           uint32_t p_full, int vec_ok) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  static_assert(P >= 10 && P <= 15, "block size");
+  constexpr int RA = P - 10, NSUB = 1 << RA, NWARPS = THREADS / 32;
+  constexpr uint32_t p = P, n4 = 1u << P;
+  const uint32_t hb = blockIdx.x + (uint32_t)(rg.lo >> p), col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  const uint32_t D = (INPLACE ? p_full : p) + beta, K = D - 1;
+  const uint32_t w_lo = rg.log >= p ? 0u : (uint32_t)(rg.lo & (n4 - 1));
+  const uint32_t w_n = rg.log >= p ? n4 : (1u << rg.log);
+  const bool full = w_n == n4 && vec_ok;
+  uint32_t *out = eval + ((blob * 4 + col) << rg.log) + ((ptrdiff_t)((size_t)hb << p) - (ptrdiff_t)rg.lo);
+  const uint32_t *c = INPLACE ? out : coef + (blob * 4 + col) * (size_t)n4;
+  if ((uint64_t)n_felts <= ((uint64_t)col << (INPLACE ? p_full : p))) {  // all-zero column
+    if (INPLACE) return;  // the first strided pass already wrote the zeros
+    for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
+    return;
+  }
+  // doubled-twiddle row of line layer i, offset to this block
+  auto blk_row = [&](int i) -> const uint32_t * {
+    return tt.blk2(1u << (K - i)) + ((size_t)hb << (P - i - 1));
+  };
+  if constexpr (RA > 0) {
+    uint32_t ta[NSUB - 1];
+#pragma unroll
+    for (int s = 0; s < RA; s++)
+#pragma unroll
+      for (int q = 0; q < (1 << s); q++) ta[(1 << s) - 1 + q] = __ldg(blk_row(P - 1 - s) + q);
+    // the loads of task it+1 are issued before the arithmetic of task it
+    constexpr int ITER = 1024 / THREADS;
+    uint32_t nxt[NSUB];
+#pragma unroll
+    for (int j = 0; j < NSUB; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + threadIdx.x);
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+      const uint32_t low = threadIdx.x + it * THREADS;
+      uint32_t v[NSUB];
+#pragma unroll
+      for (int j = 0; j < NSUB; j++) v[j] = nxt[j];
+      if (it + 1 < ITER) {
+#pragma unroll
+        for (int j = 0; j < NSUB; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + low + THREADS);
+      }
+      reg_stages_held<NSUB, RA>(v, ta);
+      uint32_t *dst = sm + low + ((low >> 5) << 2);
+#pragma unroll
+      for (int j = 0; j < NSUB; j++) dst[j * LDE_SUB] = v[j];
+    }
+    __syncthreads();
+  }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (uint32_t sub = warp; sub < (uint32_t)NSUB; sub += NWARPS) {
+    uint32_t *base = sm + sub * LDE_SUB;
+    uint32_t v[32];
+    // ---- B: layers 9..5; register k of this lane is local index (k << 5) | lane
+    if constexpr (RA > 0) {
+#pragma unroll
+      for (int k = 0; k < 32; k++) v[k] = base[k * LDE_ROW + lane];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; k++) v[k] = __ldg(c + (k << 5) + lane);
+    }
+    reg_stages_vec<32, 5>(v, 9, [&](int i) { return blk_row(i) + ((size_t)sub << (9 - i)); });
+#pragma unroll
+    for (int k = 0; k < 32; k++) base[k * LDE_ROW + lane] = v[k];
+    __syncwarp();
+    // ---- C: layers 4..1 and the circle layer; register m of this lane is local index (lane << 5) | m
+    const uint32_t *rowp = base + lane * LDE_ROW;
+#pragma unroll
+    for (int m = 0; m < 32; m += 4) {
+      uint4 q = *reinterpret_cast<const uint4 *>(rowp + m);
+      v[m] = q.x; v[m + 1] = q.y; v[m + 2] = q.z; v[m + 3] = q.w;
+    }
+    reg_stages_vec<32, 4>(v, 4, [&](int i) {
+      return blk_row(i) + ((size_t)sub << (9 - i)) + ((size_t)lane << (4 - i));
+    });
+    {
+      // 16 circle butterflies: pair index h = (global index) >> 1 starts at a multiple of 16, so
+      // the [y, -y, -x, x] pattern over 4 consecutive (x, y) pairs of the first line row is static
+      const uint32_t *cp = tt.blk2(1u << (K - 1)) + 2 * (((size_t)hb << (P - 3)) + ((size_t)sub << 7) + (lane << 2));
+      uint32_t xy[8];
+      load_tw_vec<8>(cp, xy);
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const uint32_t x2 = xy[2 * m], y2 = xy[2 * m + 1];
+        bfly_t2(v[8 * m + 0], v[8 * m + 1], y2);
+        bfly_t2_swapped(v[8 * m + 2], v[8 * m + 3], y2);
+        bfly_t2_swapped(v[8 * m + 4], v[8 * m + 5], x2);
+        bfly_t2(v[8 * m + 6], v[8 * m + 7], x2);
+      }
+    }
+    const uint32_t idx0 = (sub << 10) | (lane << 5);
+    if (full) {
+      // back through this lane's row, then 8 fully coalesced 512-byte pieces (a lane-strided
+      // 32-byte store costs the LSU data pipe 8x the wavefronts of a coalesced one)
+      uint32_t *roww = base + lane * LDE_ROW;
+#pragma unroll
+      for (int m = 0; m < 32; m += 4) *reinterpret_cast<uint4 *>(roww + m) = make_uint4(v[m], v[m + 1], v[m + 2], v[m + 3]);
+      __syncwarp();
+      uint32_t *o = out + (sub << 10) + (lane << 2);
+      const uint32_t *src = base + (lane >> 3) * LDE_ROW + ((lane & 7) << 2);
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        *reinterpret_cast<uint4 *>(o + 128 * r) = *reinterpret_cast<const uint4 *>(src + 4 * r * LDE_ROW);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 32; m++) {
+        uint32_t i = idx0 + m;
+        if (i >= w_lo && i < w_lo + w_n) out[i] = v[m];
+      }
+    }
+  }
 }
 
 // poly_log 0: one coefficient per column; every layer is a replication.
@@ -540,11 +738,33 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     cudaFuncSetAttribute(lde_block_kernel<15, 1024, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_set = true;
   }
+  static int variant = -1;
+  if (variant < 0) {
+    const char *ev = std::getenv("FRIEDA_LDE_VARIANT");  // 0 = lde_block_kernel everywhere (A/B probes)
+    variant = ev ? std::atoi(ev) : 1;
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+  }
+  const int vec_ok = (reinterpret_cast<uintptr_t>(eval) & 31) == 0;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
     const uint32_t *cf = coef + b0 * ((size_t)4 << p);
     uint32_t *ev = eval + b0 * ((size_t)4 << rg.log);
-    if (p <= LDE_SMEM_LOG_MAX) {
+    if (variant != 0 && p >= 10 && p <= LDE_SMEM_LOG_MAX) {
+      dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
+#define FR_LDE_WARP(PP, TT)                                                                                   \
+  case PP:                                                                                                    \
+    lde_warp_kernel<PP, TT, false><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, tt, rg, \
+                                                                                          p, vec_ok);          \
+    break;
+      switch (p) {
+        FR_LDE_WARP(10, 32) FR_LDE_WARP(11, 64) FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256)
+        FR_LDE_WARP(15, 512)
+      }
+#undef FR_LDE_WARP
+    } else if (p <= LDE_SMEM_LOG_MAX) {
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
       size_t smem = ((size_t)4 << p) + (((size_t)4 << p) >> 4) + 64;  // + 4 pad words per 64
 #define FR_LDE_CASE(PP, TT) \
@@ -580,6 +800,15 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       }
       dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
       size_t smem = ((size_t)4 << c) + (((size_t)4 << c) >> 4) + 64;
+      if (variant != 0) {
+#define FR_LDE_WARP(PP, TT)                                                                                  \
+  case PP:                                                                                                   \
+    lde_warp_kernel<PP, TT, true><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, tt, rg, \
+                                                                                         p, vec_ok);          \
+    break;
+        switch (c) { FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256) FR_LDE_WARP(15, 512) }
+#undef FR_LDE_WARP
+      } else
       switch (c) {
         case 12: lde_block_kernel<12, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
         case 13: lde_block_kernel<13, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
