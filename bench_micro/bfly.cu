@@ -1,0 +1,116 @@
+// Microbenchmark: the M31 radix-2 butterfly (a, b, t) -> (a + b t, a - b t) as the LDE kernels
+// issue it, in registers only (radix-32 passes, 16 independent butterflies per stage), in several
+// formulations.  Prints clocks per warp-butterfly per SM sub-partition: the arithmetic floor of the
+// circle-FFT pass.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "../frieda_b200/csrc/m31.cuh"
+using namespace frieda;
+
+// V0: IMAD.WIDE + LEA.HI + min, add + min, sub + min (what lde.cu uses)
+__device__ __forceinline__ void bf0(uint32_t &a, uint32_t &b, uint32_t t2) {
+  uint32_t tmp = m31_mul_t2(b, t2), va = a;
+  a = m31_add(va, tmp);
+  b = m31_sub(va, tmp);
+}
+// V1: Shoup: q = hi(b * t'), r = b * t - q * P (all IMAD), r in [0, 2P)
+__device__ __forceinline__ void bf1(uint32_t &a, uint32_t &b, uint32_t t, uint32_t tp) {
+  uint32_t q = __umulhi(b, tp);
+  uint32_t r = b * t - q * P31;
+  r = umin32(r, r - P31);
+  uint32_t va = a;
+  a = m31_add(va, r);
+  b = m31_sub(va, r);
+}
+// V2: as V0 but the two adds forced onto the ALU pipe (IADD3 via inline asm add)
+__device__ __forceinline__ void bf2(uint32_t &a, uint32_t &b, uint32_t t2) {
+  uint32_t tmp = m31_mul_t2(b, t2), va = a, s, d;
+  asm("add.u32 %0, %1, %2;" : "=r"(s) : "r"(va), "r"(tmp));
+  asm("sub.u32 %0, %1, %2;" : "=r"(d) : "r"(va), "r"(tmp));
+  a = umin32(s, s - P31);
+  b = umin32(d, d + P31);
+}
+// V3: the product reduced by AND/shift instead of the doubled twiddle (undoubled t)
+__device__ __forceinline__ void bf3(uint32_t &a, uint32_t &b, uint32_t t) {
+  uint32_t tmp = m31_mul(b, t), va = a;
+  a = m31_add(va, tmp);
+  b = m31_sub(va, tmp);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(uint32_t *out, const uint32_t *tw, int iters) {
+  uint32_t v[32], t[31], tp[31];
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = (threadIdx.x * 2654435761u + j * 40503u + blockIdx.x) & 0x7ffffffeu;
+#pragma unroll
+  for (int j = 0; j < 31; j++) {
+    t[j] = tw[j];
+    tp[j] = tw[31 + j];
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int half = 16 >> s;
+#pragma unroll
+      for (int q = 0; q < (1 << s); q++)
+#pragma unroll
+        for (int kk = 0; kk < half; kk++) {
+          uint32_t &a = v[q * 2 * half + kk], &b = v[q * 2 * half + kk + half];
+          const int ti = (1 << s) - 1 + q;
+          if (MODE == 0) bf0(a, b, t[ti]);
+          if (MODE == 1) bf1(a, b, t[ti], tp[ti]);
+          if (MODE == 2) bf2(a, b, t[ti]);
+          if (MODE == 3) bf3(a, b, t[ti]);
+        }
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) x ^= v[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+template <int MODE>
+void run(const char *name, uint32_t *out, const uint32_t *tw, int clock_khz, int n_sm, int ctas_per_sm) {
+  const int iters = 400, blocks = n_sm * ctas_per_sm, threads = 256;
+  k<MODE><<<blocks, threads>>>(out, tw, 4);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k<MODE><<<blocks, threads>>>(out, tw, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  double warp_bf = (double)blocks * (threads / 32) * iters * 80.0;
+  double clk = ms * 1e-3 * clock_khz * 1e3;
+  printf("%-44s %d CTA/SM  %8.3f ms  %6.2f clk per warp-butterfly per SMSP\n", name, ctas_per_sm, ms,
+         clk * (n_sm * 4) / warp_bf);
+}
+
+int main() {
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, 0);
+  int clock_khz = 0;
+  cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0);
+  printf("%s  SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, clock_khz);
+  int n = p.multiProcessorCount;
+  uint32_t *out, *tw;
+  cudaMalloc(&out, 4 * 256 * n * 8);
+  uint32_t h[62];
+  for (int j = 0; j < 62; j++) h[j] = (0x12345u * (j + 3) * 2654435761u) & 0x7ffffffeu;
+  cudaMalloc(&tw, sizeof h);
+  cudaMemcpy(tw, h, sizeof h, cudaMemcpyHostToDevice);
+  for (int c : {3, 6}) {
+    run<0>("V0 WIDE+LEA.HI, IMAD adds (lde.cu)", out, tw, clock_khz, n, c);
+    run<1>("V1 Shoup (IMAD.HI + 2 IMAD)", out, tw, clock_khz, n, c);
+    run<2>("V2 adds on the ALU pipe", out, tw, clock_khz, n, c);
+    run<3>("V3 undoubled twiddle (AND + shift reduce)", out, tw, clock_khz, n, c);
+  }
+  return 0;
+}

@@ -73,7 +73,7 @@ struct Plan {
   size_t o_in = 0, o_in2 = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
   size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
   size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
-  size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_offsets = 0, o_totals = 0,
+  size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_lvl = 0, o_offsets = 0, o_totals = 0,
          o_evals = 0;
   size_t total = 0;
 };
@@ -321,6 +321,7 @@ void layout_prove_tail(Plan &pl, uint32_t n_queries) {
   pl.o_nuniq = bp.take(pl.B * 4);
   pl.o_counts = bp.take(pl.B * pl.g.n_layers * 2 * 4);
   pl.o_offsets = bp.take(pl.B * pl.g.n_layers * 2 * 8);
+  pl.o_lvl = bp.take(pl.B * pl.g.n_layers * (size_t)pl.g.D * 4);
   pl.o_evals = bp.take(pl.B * n_queries * sizeof(QM31));
   pl.total = bp.off;
 }
@@ -810,10 +811,12 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     }
     dp.counts = at<uint32_t>(ctx, w.o_counts);
     dp.offsets = at<unsigned long long>(ctx, w.o_offsets);
+    dp.lvl = at<uint32_t>(ctx, w.o_lvl);
+    dp.lvl_stride = g.D;
     dp.evals_out = at<QM31>(ctx, w.o_evals);
     unsigned long long *d_totals = at<unsigned long long>(ctx, w.o_totals);
     KL("decommit_count", launch_decommit_count(ctx->stream, dp, nb), 1);
-    KL("decommit_scan", launch_decommit_scan(ctx->stream, dp, nb, d_totals), 1);
+    KL("decommit_scan", launch_decommit_scan(ctx->stream, dp, nb, d_totals), 2);
     unsigned long long totals[2] = {0, 0};
     CU(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
     tr.mark("grind+decommit launches");

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__rest
   uint32_t d[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) d[i] = chan[blob].digest[i];
+  const uint32_t low_mask = pow_bits >= 32 ? 0xffffffffu : ((1u << pow_bits) - 1u);
   for (;;) {
     unsigned long long start = 0, cur = 0;
     if (lane == 0) {
@@ -45,7 +46,20 @@ __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__rest
       for (int i = 0; i < 8; i++) h[i] = d[i];
       uint32_t m[16] = {(uint32_t)nonce, (uint32_t)(nonce >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       blake2s_compress_t<0x0003u>(h, m, 0, 0, 0, 0, one);  // only the two nonce words are non-zero
-      if (digest_trailing_zeros(h) >= pow_bits) atomicMin(best + blob, (unsigned long long)nonce);
+      // The screen reads digest word 0 only, so everything of the last round that does not feed
+      // v0 / v8 (two whole G functions and the tails of four more) is dead code in this loop.
+      if ((h[0] & low_mask) == 0) {
+        // rare (2^-min(pow_bits, 32) per nonce): the whole digest for the exact trailing-zero count;
+        // the nonce goes through an opaque asm so this copy is not merged with the screen above
+        uint32_t lo = (uint32_t)nonce, hi = (uint32_t)(nonce >> 32);
+        asm volatile("" : "+r"(lo), "+r"(hi));
+        uint32_t g[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = d[i];
+        uint32_t m2[16] = {lo, hi, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        blake2s_compress_t<0x0003u>(g, m2, 0, 0, 0, 0, one);
+        if (digest_trailing_zeros(g) >= pow_bits) atomicMin(best + blob, (unsigned long long)nonce);
+      }
     }
   }
 }
@@ -108,101 +122,132 @@ cudaError_t launch_queries(cudaStream_t st, Channel *chan, const unsigned long l
 // their QM31 value to fri_witness.  The Merkle multi-proof walks the levels k = d-2 .. 0: node n
 // of level k is on the path iff some query has q >> (l + d - k) == n; each of its children
 // (level k+1) that is not on the path contributes its hash to hash_witness (left, then right).
-// All lists are shifts of the one sorted query array, so the walk needs no scratch storage.
-template <bool WRITE>
-__device__ void decommit_layer(const DecommitParams &p, size_t blob, uint32_t layer, uint32_t *n_fri_out,
-                               uint32_t *n_hash_out) {
-  const uint32_t *q = p.queries + blob * p.n_queries;
-  const uint32_t nq = p.n_unique[blob];
-  const uint32_t d = p.D - layer;
-  const uint32_t *cols = p.cols[layer] + blob * p.cols_stride[layer];
-  const uint4 *tree = reinterpret_cast<const uint4 *>(p.tree[layer]) + 2 * blob * p.tree_stride[layer];
-  QM31 *fri = nullptr;
-  uint4 *hw = nullptr;
-  if (WRITE) {
-    const unsigned long long *off = p.offsets + (blob * p.n_layers + layer) * 2;
-    fri = p.fri_out + off[0];
-    hw = reinterpret_cast<uint4 *>(p.hash_out) + 2 * off[1];
-  }
-  uint32_t n_fri = 0, n_hash = 0;
-  const size_t n = (size_t)1 << d;
-  // fri witness: sibling positions that are not themselves queried
-  {
-    uint32_t i = 0;
-    while (i < nq) {
-      uint32_t g = q[i] >> (layer + 1);
-      bool has0 = false, has1 = false;
-      while (i < nq && (q[i] >> (layer + 1)) == g) {
-        if ((q[i] >> layer) & 1u) has1 = true; else has0 = true;
-        i++;
-      }
-      for (uint32_t s = 0; s < 2; s++) {
-        if (s == 0 ? has0 : has1) continue;
-        if (WRITE) {
-          size_t pos = 2 * (size_t)g + s;
-          fri[n_fri] = {{cols[pos], cols[n + pos], cols[2 * n + pos], cols[3 * n + pos]}};
-        }
-        n_fri++;
-      }
+// All lists are shifts of the one sorted query array, so every (blob, layer, walk) is independent:
+// one thread per walk, walk 0 = the fri witness, walk j >= 1 = tree level k = d - 1 - j.  A count
+// pass, a scan (per layer, then over all layers of the wave) and a write pass that repeats the walk
+// with its output offset known.
+// Runs of equal (q >> sh): every run yields the children (bit sh-1) that no query covers.
+template <class Emit>
+__device__ __forceinline__ uint32_t walk_runs(const uint32_t *__restrict__ q, uint32_t nq, uint32_t sh, Emit emit) {
+  uint32_t cnt = 0, i = 0;
+  while (i < nq) {
+    const uint32_t node = sh >= 32 ? 0u : q[i] >> sh;
+    bool has0 = false, has1 = false;
+    while (i < nq && (sh >= 32 ? 0u : q[i] >> sh) == node) {
+      if ((q[i] >> (sh - 1)) & 1u) has1 = true; else has0 = true;
+      i++;
     }
+    if (!has0) { emit(cnt, node, 0u); cnt++; }
+    if (!has1) { emit(cnt, node, 1u); cnt++; }
   }
-  // hash witness
-  for (int k = (int)d - 2; k >= 0; k--) {
-    const uint32_t sh = layer + d - (uint32_t)k;  // node = q >> sh ; child = q >> (sh - 1)
-    uint32_t i = 0;
-    while (i < nq) {
-      uint32_t node = q[i] >> sh;
-      bool has0 = false, has1 = false;
-      while (i < nq && (q[i] >> sh) == node) {
-        if ((q[i] >> (sh - 1)) & 1u) has1 = true; else has0 = true;
-        i++;
-      }
-      for (uint32_t s = 0; s < 2; s++) {
-        if (s == 0 ? has0 : has1) continue;
-        if (WRITE) {
-          size_t slot = ((size_t)1 << (k + 1)) + 2 * (size_t)node + s;
-          hw[2 * (size_t)n_hash] = tree[2 * slot];
-          hw[2 * (size_t)n_hash + 1] = tree[2 * slot + 1];
-        }
-        n_hash++;
-      }
-    }
-  }
-  *n_fri_out = n_fri;
-  *n_hash_out = n_hash;
+  return cnt;
 }
 
-__global__ void decommit_count_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// lvl[(blob * n_layers + layer) * lvl_stride + walk]: count of the walk, turned into the exclusive
+// prefix inside the layer's hash witness by the scan (walk 0, the fri witness, starts its own list).
+__global__ void __launch_bounds__(128) decommit_count_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = t / p.lvl_stride;  // (blob, layer)
+  const uint32_t walk = (uint32_t)(t % p.lvl_stride);
   if (g >= n_blobs * p.n_layers) return;
-  size_t blob = g / p.n_layers;
-  uint32_t layer = (uint32_t)(g % p.n_layers);
-  uint32_t nf, nh;
-  decommit_layer<false>(p, blob, layer, &nf, &nh);
-  p.counts[g * 2] = nf;
-  p.counts[g * 2 + 1] = nh;
+  const size_t blob = g / p.n_layers;
+  const uint32_t layer = (uint32_t)(g % p.n_layers);
+  const uint32_t d = p.D - layer;
+  uint32_t c = 0;
+  if (walk < d) {
+    const uint32_t sh = walk == 0 ? layer + 1 : layer + 1 + walk;  // walk j: node = q >> (layer + d - k), k = d-1-j
+    c = walk_runs(p.queries + blob * p.n_queries, p.n_unique[blob], sh, [](uint32_t, uint32_t, uint32_t) {});
+  }
+  p.lvl[t] = c;
 }
-__global__ void decommit_scan_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs,
-                                     unsigned long long *totals) {
-  // tiny: a single thread walks blob-major, layer-minor
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+
+// One thread per (blob, layer) sums its walks; one CTA then scans the wave.
+__global__ void __launch_bounds__(128) decommit_layer_sum_kernel(const __grid_constant__ DecommitParams p,
+                                                                 size_t n_blobs) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_blobs * p.n_layers) return;
+  uint32_t *lv = p.lvl + g * p.lvl_stride;
+  const uint32_t d = p.D - (uint32_t)(g % p.n_layers);
+  uint32_t run = 0;
+  for (uint32_t j = 1; j < d; j++) {
+    uint32_t c = lv[j];
+    lv[j] = run;
+    run += c;
+  }
+  p.counts[g * 2] = lv[0];
+  p.counts[g * 2 + 1] = run;
+}
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) decommit_scan_kernel(const __grid_constant__ DecommitParams p,
+                                                                     size_t n_blobs, unsigned long long *totals) {
+  // blob-major, layer-minor exclusive scan of both counters: contiguous chunk per thread,
+  // Hillis-Steele over the chunk sums in shared memory
+  __shared__ unsigned long long sf[SCAN_THREADS], sh[SCAN_THREADS];
+  const size_t N = n_blobs * p.n_layers;
+  const size_t chunk = (N + SCAN_THREADS - 1) / SCAN_THREADS;
+  const size_t lo = (size_t)threadIdx.x * chunk, hi = lo + chunk < N ? lo + chunk : N;
   unsigned long long f = 0, h = 0;
-  for (size_t g = 0; g < n_blobs * p.n_layers; g++) {
-    p.offsets[g * 2] = f;
-    p.offsets[g * 2 + 1] = h;
+  for (size_t g = lo; g < hi; g++) {
     f += p.counts[g * 2];
     h += p.counts[g * 2 + 1];
   }
-  totals[0] = f;
-  totals[1] = h;
+  sf[threadIdx.x] = f;
+  sh[threadIdx.x] = h;
+  __syncthreads();
+  for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+    unsigned long long af = 0, ah = 0;
+    if ((int)threadIdx.x >= off) {
+      af = sf[threadIdx.x - off];
+      ah = sh[threadIdx.x - off];
+    }
+    __syncthreads();
+    sf[threadIdx.x] += af;
+    sh[threadIdx.x] += ah;
+    __syncthreads();
+  }
+  unsigned long long bf = sf[threadIdx.x] - f, bh = sh[threadIdx.x] - h;  // exclusive
+  for (size_t g = lo; g < hi; g++) {
+    p.offsets[g * 2] = bf;
+    p.offsets[g * 2 + 1] = bh;
+    bf += p.counts[g * 2];
+    bh += p.counts[g * 2 + 1];
+  }
+  if (threadIdx.x == SCAN_THREADS - 1) {
+    totals[0] = sf[threadIdx.x];
+    totals[1] = sh[threadIdx.x];
+  }
 }
-__global__ void decommit_write_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+__global__ void __launch_bounds__(128) decommit_write_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = t / p.lvl_stride;
+  const uint32_t walk = (uint32_t)(t % p.lvl_stride);
   if (g >= n_blobs * p.n_layers) return;
-  size_t blob = g / p.n_layers;
-  uint32_t layer = (uint32_t)(g % p.n_layers);
-  uint32_t nf, nh;
-  decommit_layer<true>(p, blob, layer, &nf, &nh);
+  const size_t blob = g / p.n_layers;
+  const uint32_t layer = (uint32_t)(g % p.n_layers);
+  const uint32_t d = p.D - layer;
+  if (walk >= d) return;
+  const uint32_t *q = p.queries + blob * p.n_queries;
+  const uint32_t nq = p.n_unique[blob];
+  const unsigned long long *off = p.offsets + g * 2;
+  if (walk == 0) {
+    const uint32_t *cols = p.cols[layer] + blob * p.cols_stride[layer];
+    const size_t n = (size_t)1 << d;
+    QM31 *fri = p.fri_out + off[0];
+    walk_runs(q, nq, layer + 1, [&](uint32_t at, uint32_t node, uint32_t s) {
+      const size_t pos = 2 * (size_t)node + s;
+      fri[at] = {{cols[pos], cols[n + pos], cols[2 * n + pos], cols[3 * n + pos]}};
+    });
+  } else {
+    const uint32_t k = d - 1 - walk;
+    const uint4 *tree = reinterpret_cast<const uint4 *>(p.tree[layer]) + 2 * blob * p.tree_stride[layer];
+    uint4 *hw = reinterpret_cast<uint4 *>(p.hash_out) + 2 * (off[1] + p.lvl[t]);
+    walk_runs(q, nq, layer + 1 + walk, [&](uint32_t at, uint32_t node, uint32_t s) {
+      const size_t slot = ((size_t)1 << (k + 1)) + 2 * (size_t)node + s;
+      hw[2 * (size_t)at] = tree[2 * slot];
+      hw[2 * (size_t)at + 1] = tree[2 * slot + 1];
+    });
+  }
 }
 // evaluations at the query positions, ascending (src/proof.rs:62-66)
 __global__ void evaluations_kernel(const __grid_constant__ DecommitParams p, size_t n_blobs) {
@@ -218,18 +263,21 @@ __global__ void evaluations_kernel(const __grid_constant__ DecommitParams p, siz
 }
 
 cudaError_t launch_decommit_count(cudaStream_t st, const DecommitParams &p, size_t n_blobs) {
-  size_t n = n_blobs * p.n_layers;
-  decommit_count_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(p, n_blobs);
+  if (p.lvl_stride < p.D) return cudaErrorInvalidValue;
+  size_t n = n_blobs * p.n_layers * p.lvl_stride;
+  decommit_count_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, n_blobs);
   return cudaGetLastError();
 }
 cudaError_t launch_decommit_scan(cudaStream_t st, const DecommitParams &p, size_t n_blobs,
                                  unsigned long long *totals) {
-  decommit_scan_kernel<<<1, 32, 0, st>>>(p, n_blobs, totals);
+  size_t n = n_blobs * p.n_layers;
+  decommit_layer_sum_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, n_blobs);
+  decommit_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(p, n_blobs, totals);
   return cudaGetLastError();
 }
 cudaError_t launch_decommit_write(cudaStream_t st, const DecommitParams &p, size_t n_blobs) {
-  size_t n = n_blobs * p.n_layers;
-  decommit_write_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(p, n_blobs);
+  size_t n = n_blobs * p.n_layers * p.lvl_stride;
+  decommit_write_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, n_blobs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   size_t ne = n_blobs * p.n_queries;

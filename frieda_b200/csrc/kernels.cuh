@@ -130,6 +130,8 @@ struct DecommitParams {
   const uint8_t *tree[32];
   size_t tree_stride[32];
   uint32_t *counts;         // [blob][n_layers][2] = (n_fri_witness, n_hash_witness)
+  uint32_t *lvl;            // [blob][n_layers][lvl_stride]: per-walk counts, then prefixes inside the layer
+  uint32_t lvl_stride;      // >= D (walk 0 = fri witness, walk j = tree level d-1-j)
   unsigned long long *offsets; // [blob][n_layers][2] element offsets into fri_out / hash_out
   QM31 *fri_out;
   uint8_t *hash_out;

@@ -372,12 +372,56 @@ __device__ __forceinline__ void reg_stage(uint32_t (&v)[N], const uint32_t *t2) 
     for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2[q]);
 }
 
-// stages S .. NST-1 with all twiddles in one register array (stage s at t[2^s - 1 ..])
-template <int N, int NST, int S = 0>
+// stages S .. NST-1 with all twiddles in one register array (stage s at t[2^s - 1 ..]).  The first
+// SKIP stages have a structurally zero second operand (zero-padded coefficients): a + 0 t = a - 0 t.
+template <int N, int NST, int SKIP, int S = 0>
 __device__ __forceinline__ void reg_stages_held(uint32_t (&v)[N], const uint32_t *t) {
   if constexpr (S < NST) {
-    reg_stage<N, S>(v, t + ((1 << S) - 1));
-    reg_stages_held<N, NST, S + 1>(v, t);
+    if constexpr (S < SKIP) {
+      constexpr int half = N >> (S + 1);
+#pragma unroll
+      for (int q = 0; q < (1 << S); q++)
+#pragma unroll
+        for (int k = 0; k < half; k++) v[q * 2 * half + k + half] = v[q * 2 * half + k];
+    } else {
+      reg_stage<N, S>(v, t + ((1 << S) - 1));
+    }
+    reg_stages_held<N, NST, SKIP, S + 1>(v, t);
+  }
+}
+
+// Phase A of lde_warp_kernel: layers P-1 .. 10 for the 1024 low positions, results to shared memory.
+// The loads of task it+1 are issued before the arithmetic of task it (register budget permitting).
+template <int P, int THREADS, int SKIP>
+__device__ __forceinline__ void lde_phase_a(const uint32_t *__restrict__ c, uint32_t *sm, const uint32_t *ta) {
+  constexpr int RA = P - 10, NSUB = 1 << RA, NLOAD = NSUB >> SKIP;  // rows >= NLOAD are zero padding
+  constexpr int LDE_SUB_ = 32 * 36;
+  constexpr bool PREFETCH = NSUB <= 16;
+  uint32_t nxt[PREFETCH ? NLOAD : 1];
+  if constexpr (PREFETCH) {
+#pragma unroll
+    for (int j = 0; j < NLOAD; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + threadIdx.x);
+  }
+#pragma unroll 1
+  for (uint32_t low = threadIdx.x; low < 1024; low += THREADS) {
+    uint32_t v[NSUB];
+#pragma unroll
+    for (int j = NLOAD; j < NSUB; j++) v[j] = 0u;
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int j = 0; j < NLOAD; j++) v[j] = nxt[j];
+      if (low + THREADS < 1024) {
+#pragma unroll
+        for (int j = 0; j < NLOAD; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + low + THREADS);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NLOAD; j++) v[j] = __ldg(c + ((uint32_t)j << 10) + low);
+    }
+    reg_stages_held<NSUB, RA, SKIP>(v, ta);
+    uint32_t *dst = sm + low + ((low >> 5) << 2);
+#pragma unroll
+    for (int j = 0; j < NSUB; j++) dst[j * LDE_SUB_] = v[j];
   }
 }
 
@@ -414,8 +458,24 @@ __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef,
   const uint32_t *c = INPLACE ? out : coef + (blob * 4 + col) * (size_t)n4;
   if ((uint64_t)n_felts <= ((uint64_t)col << (INPLACE ? p_full : p))) {  // all-zero column
     if (INPLACE) return;  // the first strided pass already wrote the zeros
-    for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
+    if (full) {
+      for (uint32_t i = threadIdx.x * 4; i < n4; i += THREADS * 4)
+        *reinterpret_cast<uint4 *>(out + i) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (uint32_t i = threadIdx.x; i < w_n; i += THREADS) out[w_lo + i] = 0u;
+    }
     return;
+  }
+  // Coefficients at index >= nz are zero padding (src/utils.rs:23-24), so the second operand of the
+  // first P - ceil(log2 nz) layers is zero: those layers only replicate (a function of the input
+  // length, not of the data).
+  uint32_t skip = 0;
+  if (!INPLACE && RA > 0) {
+    const uint64_t rest = (uint64_t)n_felts - ((uint64_t)col << p);
+    if (rest < n4) {
+      const uint32_t lg = rest <= 1 ? 0u : 32u - __clz((uint32_t)rest - 1u);  // ceil(log2 rest)
+      skip = p - lg < (uint32_t)RA ? p - lg : (uint32_t)RA;
+    }
   }
   // doubled-twiddle row of line layer i, offset to this block
   auto blk_row = [&](int i) -> const uint32_t * {
@@ -427,25 +487,13 @@ __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef,
     for (int s = 0; s < RA; s++)
 #pragma unroll
       for (int q = 0; q < (1 << s); q++) ta[(1 << s) - 1 + q] = __ldg(blk_row(P - 1 - s) + q);
-    // the loads of task it+1 are issued before the arithmetic of task it
-    constexpr int ITER = 1024 / THREADS;
-    uint32_t nxt[NSUB];
-#pragma unroll
-    for (int j = 0; j < NSUB; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + threadIdx.x);
-#pragma unroll
-    for (int it = 0; it < ITER; it++) {
-      const uint32_t low = threadIdx.x + it * THREADS;
-      uint32_t v[NSUB];
-#pragma unroll
-      for (int j = 0; j < NSUB; j++) v[j] = nxt[j];
-      if (it + 1 < ITER) {
-#pragma unroll
-        for (int j = 0; j < NSUB; j++) nxt[j] = __ldg(c + ((uint32_t)j << 10) + low + THREADS);
-      }
-      reg_stages_held<NSUB, RA>(v, ta);
-      uint32_t *dst = sm + low + ((low >> 5) << 2);
-#pragma unroll
-      for (int j = 0; j < NSUB; j++) dst[j * LDE_SUB] = v[j];
+    switch (skip) {
+      case 0: lde_phase_a<P, THREADS, 0>(c, sm, ta); break;
+      case 1: lde_phase_a<P, THREADS, (RA >= 1 ? 1 : 0)>(c, sm, ta); break;
+      case 2: lde_phase_a<P, THREADS, (RA >= 2 ? 2 : 0)>(c, sm, ta); break;
+      case 3: lde_phase_a<P, THREADS, (RA >= 3 ? 3 : 0)>(c, sm, ta); break;
+      case 4: lde_phase_a<P, THREADS, (RA >= 4 ? 4 : 0)>(c, sm, ta); break;
+      default: lde_phase_a<P, THREADS, (RA >= 5 ? 5 : 0)>(c, sm, ta); break;
     }
     __syncthreads();
   }

@@ -144,7 +144,10 @@ def test_commit_batch_device_pointers(ctx, torch_mod):
 @pytest.mark.parametrize("p,beta,nz_frac", [(0, 3, 1.0), (1, 2, 1.0), (2, 1, 1.0), (1, 1, 1.0), (0, 1, 1.0), (3, 2, 1.0),
                                             (4, 2, 1.0), (5, 4, 0.6), (6, 1, 1.0), (7, 3, 1.0), (8, 1, 0.4),
                                             (9, 2, 1.0), (10, 1, 1.0), (11, 3, 0.3), (12, 1, 1.0), (13, 2, 0.7),
-                                            (14, 4, 0.53), (15, 2, 1.0), (16, 1, 0.55), (17, 2, 0.9)])
+                                            (14, 4, 0.53), (15, 2, 1.0), (16, 1, 0.55), (17, 2, 0.9),
+                                            # zero-padded columns: the top layers of the column holding the last felt only replicate
+                                            (14, 2, 0.2501), (14, 1, 0.26), (12, 2, 0.2503), (15, 1, 0.30), (13, 1, 0.5003),
+                                            (11, 2, 0.76), (10, 2, 0.27), (15, 1, 0.2500001)])
 def test_lde_pass_vs_oracle_fft(ctx, torch_mod, p, beta, nz_frac):
     torch = torch_mod
     rng = np.random.default_rng(p * 31 + beta)
