@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, const uint32_t *tw, int 
           if (MODE == 1) bf1(a, b, t[ti], tp[ti]);
           if (MODE == 2) bf2(a, b, t[ti]);
           if (MODE == 3) bf3(a, b, t[ti]);
+          if (MODE == 4) { if (kk % 3 == 2) bf1(a, b, t[ti], tp[ti]); else bf0(a, b, t[ti]); }
+          if (MODE == 5) { if (kk % 4 == 3) bf1(a, b, t[ti], tp[ti]); else bf0(a, b, t[ti]); }
+          if (MODE == 6) { if (kk % 2 == 1) bf1(a, b, t[ti], tp[ti]); else bf0(a, b, t[ti]); }
         }
     }
   }
@@ -111,6 +114,9 @@ int main() {
     run<1>("V1 Shoup (IMAD.HI + 2 IMAD)", out, tw, clock_khz, n, c);
     run<2>("V2 adds on the ALU pipe", out, tw, clock_khz, n, c);
     run<3>("V3 undoubled twiddle (AND + shift reduce)", out, tw, clock_khz, n, c);
+    run<4>("V4 mix V0:V1 2:1", out, tw, clock_khz, n, c);
+    run<5>("V5 mix V0:V1 3:1", out, tw, clock_khz, n, c);
+    run<6>("V6 mix V0:V1 1:1", out, tw, clock_khz, n, c);
   }
   return 0;
 }

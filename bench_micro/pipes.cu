@@ -56,6 +56,22 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t k1, uint32_t k2
       REP8(asm volatile("{mad.hi.u32 %0, %0, %9, %8; mad.hi.u32 %1, %1, %9, %8; mad.hi.u32 %2, %2, %9, %8; mad.hi.u32 %3, %3, %9, %8;"
                         "mad.hi.u32 %4, %4, %9, %8; mad.hi.u32 %5, %5, %9, %8; mad.hi.u32 %6, %6, %9, %8; mad.hi.u32 %7, %7, %9, %8;}"
                         : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(b), "r"(k1));)
+    } else if (MODE == 12) {  // 2:1 LOP3 : IMAD.HI
+      REP8(asm volatile("{lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; mad.hi.u32 %0, %0, %9, %8; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %1, %1, %9, %8;"
+                        "lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; mad.hi.u32 %2, %2, %9, %8; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %3, %3, %9, %8;}"
+                        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(b), "r"(k1));)
+    } else if (MODE == 13) {  // 4:1 LOP3 : IMAD.HI
+      REP8(asm volatile("{lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %0, %0, %9, %8;"
+                        "lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %1, %1, %9, %8;}"
+                        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(b), "r"(k1));)
+    } else if (MODE == 14) {  // 4:1 LOP3 : IMAD.WIDE
+      REP8(asm volatile("{.reg .b64 t; lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mul.wide.u32 t, %0, %8; mov.b64 {%0, %1}, t;"
+                        "lop3.b32 %4, %4, %8, %9, 0x96; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; lop3.b32 %7, %7, %8, %9, 0x96; mul.wide.u32 t, %2, %9; mov.b64 {%2, %3}, t;}"
+                        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(k1), "r"(k2));)
+    } else if (MODE == 15) {  // 4:2:1 LOP3 : IMAD : IMAD.HI
+      REP8(asm volatile("{lop3.b32 %4, %4, %8, %9, 0x96; mad.lo.u32 %2, %2, %9, %8; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; mad.lo.u32 %3, %3, %9, %8; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %0, %0, %9, %8;"
+                        "lop3.b32 %4, %4, %8, %9, 0x96; mad.lo.u32 %2, %2, %9, %8; lop3.b32 %5, %5, %8, %9, 0x96; lop3.b32 %6, %6, %8, %9, 0x96; mad.lo.u32 %3, %3, %9, %8; lop3.b32 %7, %7, %8, %9, 0x96; mad.hi.u32 %1, %1, %9, %8;}"
+                        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(b), "r"(k1));)
     } else if (MODE == 11) {  // 3:1 ALU : IMAD
       REP8(asm volatile("{lop3.b32 %0, %0, %8, %9, 0x96; prmt.b32 %1, %1, %1, 0x1032; shf.r.wrap.b32 %2, %2, %2, 12; mad.lo.u32 %4, %4, %9, %8; lop3.b32 %3, %3, %8, %9, 0x96; prmt.b32 %0, %0, %0, 0x1032; shf.r.wrap.b32 %1, %1, %1, 7; mad.lo.u32 %5, %5, %9, %8;"
                         "lop3.b32 %2, %2, %8, %9, 0x96; prmt.b32 %3, %3, %3, 0x0321; shf.r.wrap.b32 %0, %0, %0, 12; mad.lo.u32 %6, %6, %9, %8; lop3.b32 %1, %1, %8, %9, 0x96; prmt.b32 %2, %2, %2, 0x0321; shf.r.wrap.b32 %3, %3, %3, 7; mad.lo.u32 %7, %7, %9, %8;}"
@@ -100,5 +116,9 @@ int main() {
   run<11>("ALU:IMAD 3:1", 16, out, clock_khz, n);
   run<8>("LOP3:IMAD.WIDE 2:1", 12, out, clock_khz, n);
   run<9>("LOP3:IMAD.WIDE 1:1", 8, out, clock_khz, n);
+  run<14>("LOP3:IMAD.WIDE 4:1", 10, out, clock_khz, n);
+  run<12>("LOP3:IMAD.HI 2:1", 12, out, clock_khz, n);
+  run<13>("LOP3:IMAD.HI 4:1", 10, out, clock_khz, n);
+  run<15>("LOP3:IMAD:IMAD.HI 4:2:1", 14, out, clock_khz, n);
   return 0;
 }
