@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfrieda_b200.so")
 SOURCES = ["ctx.cu", "lde.cu", "merkle.cu", "fri.cu", "decommit.cu", "verify_batch.cu", "proof.cpp", "verify.cpp"]
+# host-only sources built by the host compiler with per-file ISA flags (entered only after a runtime CPU check)
+HOST_SOURCES = {"blake2s_x8.cpp": ["-mavx2"], "blake2s_x16.cpp": ["-mavx512f"], "cpu_features.cpp": []}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas",
@@ -42,6 +44,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src + ".o")
         cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, extra in HOST_SOURCES.items():
+        obj = os.path.join(objdir, src + ".o")
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-Wall"] + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

@@ -10,15 +10,29 @@ namespace host {
 
 constexpr uint32_t GEN_X = 2u, GEN_Y = 1268011823u;  // generator of the order-2^31 circle group
 
-// G^index, index taken mod 2^31 (LSB-first double-and-add).
-inline CPoint point_from_index(uint32_t index) {
-  CPoint res = {1u, 0u}, cur = {GEN_X, GEN_Y};
-  index &= 0x7fffffffu;
-  while (index) {
-    if (index & 1u) res = cpoint_add(res, cur);
-    cur = cpoint_add(cur, cur);
-    index >>= 1;
+// G^(2^j), j = 0..30, computed once.
+struct GenPowerTable {
+  CPoint g[31];
+  GenPowerTable() {
+    CPoint cur = {GEN_X, GEN_Y};
+    for (int j = 0; j < 31; j++) {
+      g[j] = cur;
+      cur = cpoint_add(cur, cur);
+    }
   }
+};
+inline const GenPowerTable &gen_powers() {
+  static const GenPowerTable t;
+  return t;
+}
+
+// G^index, index taken mod 2^31: one group addition per set bit.
+inline CPoint point_from_index(uint32_t index) {
+  const GenPowerTable &t = gen_powers();
+  CPoint res = {1u, 0u};
+  index &= 0x7fffffffu;
+  for (int j = 0; index; j++, index >>= 1)
+    if (index & 1u) res = cpoint_add(res, t.g[j]);
   return res;
 }
 
