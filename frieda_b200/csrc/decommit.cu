@@ -18,8 +18,12 @@ namespace frieda {
 // stops when the chunk it was handed starts above the best nonce found so far.  Every nonce below
 // the answer is examined (the minimum is exact), little above it is, and there is no host round trip.
 constexpr int GR_THREADS = 256;
-constexpr uint32_t GR_CHUNK = 128;  // nonces per grab = 4 per lane
+// nonces per grab: 4 per lane for batches; 1 per lane when a few blobs have the whole GPU to themselves
+// (every resident warp examines at least one chunk, and with 128-nonce chunks that alone is more work
+// than the expected 2^20-nonce search of the reference's benches)
+constexpr uint32_t GR_CHUNK_BATCH = 128, GR_CHUNK_SINGLE = 32;
 
+template <uint32_t GR_CHUNK>
 __global__ void __launch_bounds__(GR_THREADS) grind_kernel(const Channel *__restrict__ chan, uint32_t pow_bits,
                                                            uint64_t limit, unsigned long long *best,
                                                            unsigned long long *next, uint32_t one) {
@@ -71,8 +75,12 @@ cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits
   if (e != cudaSuccess) return e;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
-    grind_kernel<<<dim3(ctas_per_blob, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, limit, best + b0,
-                                                                          next + b0, 1u);
+    if (ctas_per_blob > 32)
+      grind_kernel<GR_CHUNK_SINGLE><<<dim3(ctas_per_blob, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, limit,
+                                                                                            best + b0, next + b0, 1u);
+    else
+      grind_kernel<GR_CHUNK_BATCH><<<dim3(ctas_per_blob, (unsigned)nb), GR_THREADS, 0, st>>>(chan + b0, pow_bits, limit,
+                                                                                           best + b0, next + b0, 1u);
   }
   return cudaGetLastError();
 }
