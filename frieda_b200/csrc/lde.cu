@@ -11,9 +11,6 @@
 // hb using the twiddles whose index has hb as its high bits.  Each (blob, column, block) is one
 // CTA working in shared memory; HBM sees the coefficients once (L2 for re-reads) and the
 // evaluations once.
-#include <cstdlib>
-#include <utility>
-
 #include "kernels.cuh"
 
 namespace frieda {
@@ -106,7 +103,8 @@ cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, ui
   return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------- LDE
+// ---------------------------------------------------------------- LDE, blocks below 2^10 points
+// (larger blocks: lde_warp_kernel further down)
 // One CTA = one (block hb, column, blob): a 2^p-point FFT, layers p-1 .. 0, done as radix-16
 // passes held in registers (4 layers per shared-memory round trip) and a last pass of
 // R_last = ((p-1) mod 4) + 1 layers over 2^R_last consecutive points whose results go straight to
@@ -470,7 +468,7 @@ __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef,
   // first P - ceil(log2 nz) layers is zero: those layers only replicate (a function of the input
   // length, not of the data).
   uint32_t skip = 0;
-  if (!INPLACE && RA > 0) {
+  if constexpr (!INPLACE && RA > 0) {
     const uint64_t rest = (uint64_t)n_felts - ((uint64_t)col << p);
     if (rest < n4) {
       const uint32_t lg = rest <= 1 ? 0u : 32u - __clz((uint32_t)rest - 1u);  // ceil(log2 rest)
@@ -771,36 +769,20 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     lde_tiny_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(coef, eval, p, D, n_cols, half_initial);
     return cudaGetLastError();
   }
-  static bool attr_set = false;
-  const int big = (4 << LDE_SMEM_LOG_MAX) + (4 << LDE_SMEM_LOG_MAX) / 16 + 64;
-  if (!attr_set) {
-    // blocks of 2^12 .. 2^15 points: passes of up to 5 layers (radix 32) with 256 threads measured fastest
-    cudaFuncSetAttribute(lde_block_kernel<12, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<13, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<14, 256, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    // 2^15-point blocks take 136 KiB of shared memory (one CTA per SM): 1024 threads, radix-16 passes
-    cudaFuncSetAttribute(lde_block_kernel<15, 1024, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<12, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<13, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<14, 256, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(lde_block_kernel<15, 1024, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    attr_set = true;
-  }
-  static int variant = -1;
-  if (variant < 0) {
-    const char *ev = std::getenv("FRIEDA_LDE_VARIANT");  // 0 = lde_block_kernel everywhere (A/B probes)
-    variant = ev ? std::atoi(ev) : 1;
+  static const bool attr_set = [] {  // blocks of 2^14 / 2^15 points need more than the default 48 KiB
     cudaFuncSetAttribute(lde_warp_kernel<14, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
     cudaFuncSetAttribute(lde_warp_kernel<14, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
     cudaFuncSetAttribute(lde_warp_kernel<15, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
     cudaFuncSetAttribute(lde_warp_kernel<15, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
-  }
+    return true;
+  }();
+  (void)attr_set;
   const int vec_ok = (reinterpret_cast<uintptr_t>(eval) & 31) == 0;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
     const uint32_t *cf = coef + b0 * ((size_t)4 << p);
     uint32_t *ev = eval + b0 * ((size_t)4 << rg.log);
-    if (variant != 0 && p >= 10 && p <= LDE_SMEM_LOG_MAX) {
+    if (p >= 10 && p <= LDE_SMEM_LOG_MAX) {
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
 #define FR_LDE_WARP(PP, TT)                                                                                   \
   case PP:                                                                                                    \
@@ -812,23 +794,18 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
         FR_LDE_WARP(15, 512)
       }
 #undef FR_LDE_WARP
-    } else if (p <= LDE_SMEM_LOG_MAX) {
+    } else if (p < 10) {
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
       size_t smem = ((size_t)4 << p) + (((size_t)4 << p) >> 4) + 64;  // + 4 pad words per 64
 #define FR_LDE_CASE(PP, TT) \
   case PP: lde_block_kernel<PP, TT, false><<<grid, TT, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-#define FR_LDE_BIG(PP) \
-  case PP: lde_block_kernel<PP, 256, false, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
       switch (p) {
         case 0: lde_copy_kernel<<<grid, 1, 0, st>>>(cf, ev, beta, n_felts, rg); break;
         FR_LDE_CASE(1, 32) FR_LDE_CASE(2, 32) FR_LDE_CASE(3, 32) FR_LDE_CASE(4, 32) FR_LDE_CASE(5, 32)
-        FR_LDE_CASE(6, 32) FR_LDE_CASE(7, 64) FR_LDE_CASE(8, 64) FR_LDE_CASE(9, 128) FR_LDE_CASE(10, 128)
-        FR_LDE_CASE(11, 256) FR_LDE_BIG(12) FR_LDE_BIG(13) FR_LDE_BIG(14)
-        case 15: lde_block_kernel<15, 1024, false, 4><<<grid, 1024, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
+        FR_LDE_CASE(6, 32) FR_LDE_CASE(7, 64) FR_LDE_CASE(8, 64) FR_LDE_CASE(9, 128)
         default: return cudaErrorInvalidValue;
       }
 #undef FR_LDE_CASE
-#undef FR_LDE_BIG
     } else {
       // m register-only radix-16 passes over layers p-1 .. c, then 2^c chunks in shared memory;
       // c = p - 4m lies in 12..15.  After the first pass everything stays inside the owned range.
@@ -847,22 +824,13 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
           lde_strided_r16_kernel<false><<<grid, 256, 0, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
       }
       dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
-      size_t smem = ((size_t)4 << c) + (((size_t)4 << c) >> 4) + 64;
-      if (variant != 0) {
 #define FR_LDE_WARP(PP, TT)                                                                                  \
   case PP:                                                                                                   \
     lde_warp_kernel<PP, TT, true><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, tt, rg, \
                                                                                          p, vec_ok);          \
     break;
-        switch (c) { FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256) FR_LDE_WARP(15, 512) }
+      switch (c) { FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256) FR_LDE_WARP(15, 512) }
 #undef FR_LDE_WARP
-      } else
-      switch (c) {
-        case 12: lde_block_kernel<12, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        case 13: lde_block_kernel<13, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        case 14: lde_block_kernel<14, 256, true, 5><<<grid, 256, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-        default: lde_block_kernel<15, 1024, true, 4><<<grid, 1024, smem, st>>>(cf, ev, beta, n_felts, tt, rg, p); break;
-      }
     }
   }
   return cudaGetLastError();

@@ -21,4 +21,4 @@ for _ in range(20): f()
 e1.record(stream); stream.synchronize()
 ms = e0.elapsed_time(e1) / 20
 b = nb * (16 * (1 << p) + 16 * (1 << D))
-print(os.environ.get("FRIEDA_LDE_VARIANT", "0"), f"lde {ms:.4f} ms  {b/ms/1e6:.0f} GB/s  {b/ms/1e6/6552:.3f}", "checksum", int(d_eval.view(torch.int64).sum().item()) & 0xffffffff)
+print(f"lde {ms:.4f} ms  {b/ms/1e6:.0f} GB/s  {b/ms/1e6/6552:.3f}", "checksum", int(d_eval.view(torch.int64).sum().item()) & 0xffffffff)
