@@ -231,6 +231,9 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL announces its version on stdout at NCCL_DEBUG=VERSION (this image's default): rank 0's stdout
+        # must carry the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = measured_peaks()
 
