@@ -225,15 +225,17 @@ def main():
     import frieda_b200 as F
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries the one JSON line and nothing else: libraries that write to fd 1 (NCCL announces its
+    # version there when its first communicator is created) go to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: frieda_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL announces its version on stdout at NCCL_DEBUG=VERSION (this image's default): rank 0's stdout
-        # must carry the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = measured_peaks()
 
@@ -393,7 +395,9 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     return 0
 
 

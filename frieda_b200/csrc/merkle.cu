@@ -19,6 +19,10 @@
 namespace frieda {
 
 constexpr int MB_THREADS = 256;
+// 4 CTAs per SM (64 registers, 48 KiB of shared memory each).  Probed on B200: forcing 5 or 6 resident CTAs
+// (48 / 40 registers, 512-leaf chunks) is 1-2 % slower -- the ALU pipe, not occupancy, bounds these kernels
+// (profiles/r01_ncu_summary.md).
+constexpr int MB_MIN_BLOCKS = 4;
 constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB + 16 KiB of shared memory
 
 struct alignas(16) Hash32 {
@@ -47,7 +51,7 @@ __device__ __forceinline__ uint32_t circle_fold_itw(const uint32_t *iblk, size_t
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(MB_THREADS) merkle_bottom_kernel(const MerkleBottomParams p) {
+__global__ void __launch_bounds__(MB_THREADS, MB_MIN_BLOCKS) merkle_bottom_kernel(const MerkleBottomParams p) {
   __shared__ Hash32 sm_a[1u << MB_CHUNK_LOG_MAX];
   __shared__ Hash32 sm_b[1u << (MB_CHUNK_LOG_MAX - 1)];
   const size_t blob = blockIdx.y;
