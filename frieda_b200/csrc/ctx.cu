@@ -333,6 +333,7 @@ size_t pick_wave(frieda_ctx *ctx, Plan &pl, size_t n, bool stage_input, uint32_t
   };
   size_t B = n > 32768 ? 32768 : n;
   // host input: at least 4 waves (of >= 128 blobs) so that all but the first upload hide behind compute
+  // (8 waves measure the same end-to-end rate, 16 are 1.5 % slower)
   if (stage_input && n >= 512 && B > (n + 3) / 4) B = (n + 3) / 4;
   lay(B);
   // fast path: the workspace we already hold fits the whole call (cudaMemGetInfo costs milliseconds)

@@ -639,12 +639,11 @@ __global__ void __launch_bounds__(256) lde_strided_r16_kernel(const uint32_t *__
   for (int s = 0; s < 4; s++) {
     const uint32_t i = top - 1 - s;
     // twiddle index of element j: (global index) >> (i + 1) = (sub << s) | (j >> (4 - s))
-    const uint32_t *tw = tt.blk(1u << (K - i)) + (sub << s);
+    const uint32_t *tw = tt.blk2(1u << (K - i)) + (sub << s);  // pre-doubled twiddles
     const int half = 8 >> s;
 #pragma unroll
     for (int q = 0; q < (1 << s); q++) {
-      uint32_t tv = __ldg(tw + q);
-      uint32_t t2 = tv + tv;
+      uint32_t t2 = __ldg(tw + q);
 #pragma unroll
       for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2);
     }
