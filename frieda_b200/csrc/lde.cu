@@ -3,7 +3,9 @@
 // Replaces, for the path of src/commit.rs:12-16 and src/proof.rs:38,44-50:
 //   utils::bytes_to_felt_le / polynomial_from_bytes   (src/utils.rs:10-33)   -> pack_kernel
 //   CpuBackend::precompute_twiddles(half_odds(K))     (src/commit.rs:15)     -> twiddle_kernel
-//   SecureCirclePoly::evaluate_with_twiddles          (src/commit.rs:16)     -> lde_block_kernel
+//   SecureCirclePoly::evaluate_with_twiddles          (src/commit.rs:16)     -> lde_warp_kernel (blocks of 2^10 ..
+//                                                        2^15 points), lde_block_kernel (smaller), lde_strided_r16_kernel
+//                                                        (the layers above 2^15-point blocks)
 //
 // LDE structure: coefficients are zero-padded at the high indices and the
 // circle FFT runs its largest strides first, so the first log_blowup layers only replicate the
@@ -332,7 +334,8 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel(const uint32_t *coef
 //      warp, fetched as 128-bit loads);
 //   -- __syncwarp (transpose through the warp's own 32 rows of 36 words) --
 //   C  layers 4 .. 1 and the circle layer on 32 consecutive points per lane (128-bit shared loads,
-//      per-lane twiddles as 128-bit loads, results to HBM as 256-bit stores).
+//      per-lane twiddles as 128-bit loads, results staged through the warp's rows and written to HBM as
+//      fully coalesced 512-byte pieces).
 // Warps drift apart after the barrier, so the load/store phases of one warp overlap the arithmetic
 // of the others.  Rows of 32 words are padded to 36: lane-consecutive scalar accesses and 128-bit
 // row accesses are both bank-conflict free.  Twiddles come pre-doubled (TwiddleTable::tw2); a
