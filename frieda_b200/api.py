@@ -92,7 +92,8 @@ EXPORTS = [
     "frieda_verify_batch_bytes",
     "frieda_verify_core_host", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
-    "frieda_commit_split_local_device",
+    "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
+    "frieda_commit_split_peers",
     "frieda_merkle_combine", "frieda_decode_block", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
@@ -145,6 +146,11 @@ def load_library(build_if_missing: bool = True):
         "frieda_commit_split_local": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_commit_split_local_device": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "frieda_merkle_combine": (C.c_int, [vp, vp, C.c_uint32, u8p]),
+        "frieda_commit_split_local_peers": (C.c_int, [vp, C.POINTER(C.c_void_p), C.c_uint32, sz, sz, C.c_uint32,
+                                                      C.c_uint32, vp]),
+        "frieda_merkle_combine_peers": (C.c_int, [vp, C.POINTER(C.c_void_p), C.c_uint32, u8p]),
+        "frieda_commit_split_peers": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), sz,
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, u8p]),
         "frieda_decode_block": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, vp]),
         "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
         "frieda_pass_lde": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp]),
@@ -280,6 +286,10 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            import sys
+            par = sys.modules.get("frieda_b200.parallel")
+            if par is not None:  # peer-mapped buffers were used on this context's stream: free them first
+                par.release_peer_memory(self)
             self._L.frieda_ctx_destroy(self._h)
             self._h = None
 
@@ -440,6 +450,34 @@ class Context:
                                   subroot_dev_ptr: int):
         self._check(self._L.frieda_commit_split_local_device(self._h, data_dev_ptr, length, log_blowup_factor, rank,
                                                              world, subroot_dev_ptr))
+
+    def commit_split_local_peers(self, peer_slice_ptrs, slice_len: int, length: int, log_blowup_factor: int,
+                                 rank: int, subroot_dev_ptr: int):
+        """Slice r of the blob is read in place from peer_slice_ptrs[r] (peer-mapped device memory).
+        Asynchronous on the context's stream."""
+        world = len(peer_slice_ptrs)
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_slice_ptrs])
+        self._check(self._L.frieda_commit_split_local_peers(self._h, arr, world, slice_len, length, log_blowup_factor,
+                                                            rank, subroot_dev_ptr))
+
+    def commit_split_peers(self, data, log_blowup_factor: int, rank: int, peer_slice_ptrs, slice_len: int,
+                           peer_root_ptrs, peer_flag_ptrs, epoch: int) -> bytes:
+        """The whole split commit of this rank in one call (frieda_commit_split_peers): exchanges over peer memory."""
+        a = _as_u8(data)
+        world = len(peer_slice_ptrs)
+        mk = lambda ps: (C.c_void_p * world)(*[int(p) for p in ps])  # noqa: E731
+        out = (C.c_uint8 * 32)()
+        self._check(self._L.frieda_commit_split_peers(self._h, a.ctypes.data, a.size, log_blowup_factor, rank, world,
+                                                      mk(peer_slice_ptrs), slice_len, mk(peer_root_ptrs),
+                                                      mk(peer_flag_ptrs), epoch, out))
+        return bytes(out)
+
+    def merkle_combine_peers(self, peer_root_ptrs) -> bytes:
+        world = len(peer_root_ptrs)
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_root_ptrs])
+        out = (C.c_uint8 * 32)()
+        self._check(self._L.frieda_merkle_combine_peers(self._h, arr, world, out))
+        return bytes(out)
 
     def merkle_combine(self, subroots_dev_ptr: int, world: int) -> bytes:
         out = (C.c_uint8 * 32)()

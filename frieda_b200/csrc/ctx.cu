@@ -122,7 +122,7 @@ struct frieda_ctx {
   uint8_t *arena = nullptr;
   size_t arena_bytes = 0;
   // small result staging
-  uint8_t *d_scratch = nullptr;  // 4 KiB
+  uint8_t *d_scratch = nullptr;  // 8 KiB: [0, 4 KiB) top-of-tree scratch (2 x 64 slots), then small flags
   // grow-only buffers of the proof path: gathered witnesses on the device, pinned readback on the host
   uint8_t *d_gather = nullptr;
   size_t d_gather_bytes = 0;
@@ -915,7 +915,7 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_scratch, 4096)) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->d_scratch, 8192)) != cudaSuccess) {
     g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e);
     cudaGetLastError();
     delete ctx;
@@ -1084,10 +1084,13 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
 // strides first, so that range is computable from the coefficient vector alone (launch_lde with an
 // owned range): no exchange of evaluations.  Only the 32-byte subtree roots travel (NCCL
 // all-gather in the host layer), then frieda_merkle_combine hashes the top g levels.
+// peers != nullptr: the input lies in `world` slices of slice_len bytes behind peer-mapped pointers, and the
+// call returns without synchronising the stream.
 static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
-                                   uint32_t rank, uint32_t world, uint8_t *d_subroot_out, bool device_input) {
+                                   uint32_t rank, uint32_t world, uint8_t *d_subroot_out, bool device_input,
+                                   const PeerPtrs *peers = nullptr, size_t slice_len = 0) {
   if (!ctx) return FRIEDA_ERR_ARG;
-  if ((!data && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
+  if ((!data && !peers && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || rank >= world) return ctx->fail_arg("world must be a power of two > rank");
   CU(cudaSetDevice(ctx->device));
   Plan pl;
@@ -1112,14 +1115,17 @@ static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t 
   if ((rc = ensure_arena(ctx, bp.off))) return rc;
   ctx->have_last = false;
   const uint8_t *d_in = data;
-  if (!device_input) {
+  if (!device_input && !peers) {
     uint8_t *stage = at<uint8_t>(ctx, o_in);
     if (len) CU(cudaMemcpyAsync(stage, data, len, cudaMemcpyHostToDevice, ctx->stream));
     d_in = stage;
   }
   uint32_t *coef = at<uint32_t>(ctx, o_coef);
   uint32_t *eval = at<uint32_t>(ctx, o_eval);
-  KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
+  if (peers)
+    KL("pack_peers", launch_pack_peers(ctx->stream, *peers, world, rank, slice_len, len, g.n_felts, g.p, coef), 1);
+  else
+    KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
   LdeRange rg{(size_t)rank << rlog, rlog};
   KL("lde", launch_lde(ctx->stream, coef, eval, g.p, g.beta, 1, g.n_felts, table(ctx), half_initial_point(g), &rg),
      (g.p > 15 ? 2 : 1));
@@ -1131,7 +1137,7 @@ static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t 
   mp.tree_stride = slots;
   if ((rc = run_tree(ctx, SRC_COLS, mp, rlog, lv, false, 1, nullptr, 0, nullptr, nullptr, 0))) return rc;
   CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (!peers) CU(cudaStreamSynchronize(ctx->stream));
   return FRIEDA_OK;
 }
 
@@ -1142,6 +1148,85 @@ int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, 
 int frieda_commit_split_local_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t log_blowup,
                                      uint32_t rank, uint32_t world, uint8_t *d_subroot_out) {
   return commit_split_local_impl(ctx, d_data, len, log_blowup, rank, world, d_subroot_out, true);
+}
+
+int frieda_commit_split_local_peers(frieda_ctx *ctx, const uint8_t *const *peer_slices, uint32_t world,
+                                    size_t slice_len, size_t len, uint32_t log_blowup, uint32_t rank,
+                                    uint8_t *d_subroot_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!peer_slices) return ctx->fail_arg("null pointer");
+  if (world == 0 || world > MAX_PEERS) return ctx->fail_arg("world must be in 1..64");
+  if (slice_len == 0 || (slice_len & 15) || (uint64_t)slice_len * world < len)
+    return ctx->fail_arg("slice_len must be a multiple of 16 with world * slice_len >= len");
+  PeerPtrs pp;
+  for (uint32_t r = 0; r < MAX_PEERS; r++) pp.p[r] = r < world ? peer_slices[r] : nullptr;
+  for (uint32_t r = 0; r < world; r++)
+    if (!pp.p[r]) return ctx->fail_arg("null peer slice");
+  return commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, d_subroot_out, true, &pp, slice_len);
+}
+
+int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
+                              uint32_t world, uint8_t *const *peer_slices, size_t slice_len,
+                              uint8_t *const *peer_roots, uint32_t *const *peer_flags, uint32_t epoch,
+                              uint8_t root_out[32]) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if ((!data && len) || !peer_slices || !peer_roots || !peer_flags || !root_out) return ctx->fail_arg("null pointer");
+  if (world == 0 || (world & (world - 1)) || world > MAX_PEERS || rank >= world)
+    return ctx->fail_arg("world must be a power of two <= 64 and > rank");
+  if (slice_len == 0 || (slice_len & 15) || (uint64_t)slice_len * world < len)
+    return ctx->fail_arg("slice_len must be a multiple of 16 with world * slice_len >= len");
+  CU(cudaSetDevice(ctx->device));
+  PeerPtrs sl, rt;
+  PeerFlags fl;
+  for (uint32_t r = 0; r < MAX_PEERS; r++) {
+    sl.p[r] = r < world ? peer_slices[r] : nullptr;
+    rt.p[r] = r < world ? peer_roots[r] : nullptr;
+    fl.p[r] = r < world ? peer_flags[r] : nullptr;
+    if (r < world && (!sl.p[r] || !rt.p[r] || !fl.p[r])) return ctx->fail_arg("null peer pointer");
+  }
+  int *d_timeout = reinterpret_cast<int *>(ctx->d_scratch + 4096);
+  CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
+  // my slice of the input, over my own PCIe link
+  const size_t lo = std::min(len, (size_t)rank * slice_len), hi = std::min(len, lo + slice_len);
+  if (hi > lo) CU(cudaMemcpyAsync(peer_slices[rank], data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+  KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 0, epoch, d_timeout), 1);
+  int rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len);
+  if (rc) return rc;
+  KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 1, epoch, d_timeout), 1);
+  uint32_t gl = 0;
+  while ((1u << gl) < world) gl++;
+  uint8_t *tree = ctx->d_scratch;  // heap order: the subtree roots are level gl
+  KL("gather_roots", launch_gather_roots(ctx->stream, rt, world, tree), 1);
+  KL("merkle_top", launch_merkle_top(ctx->stream, tree, 2 * (size_t)world, gl, 0, nullptr, 0, nullptr, nullptr, 0, 1), 1);
+  int timed_out = 0;
+  CU(cudaMemcpyAsync(root_out, tree + 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&timed_out, d_timeout, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (timed_out) {
+    ctx->err = "peer barrier timed out: a rank of the split commit did not arrive";
+    return FRIEDA_ERR_CUDA;
+  }
+  return FRIEDA_OK;
+}
+
+int frieda_merkle_combine_peers(frieda_ctx *ctx, const uint8_t *const *peer_roots, uint32_t world,
+                                uint8_t root_out[32]) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!peer_roots || !root_out) return ctx->fail_arg("null pointer");
+  if (world == 0 || (world & (world - 1)) || world > MAX_PEERS) return ctx->fail_arg("world must be a power of two <= 64");
+  CU(cudaSetDevice(ctx->device));
+  PeerPtrs pp;
+  for (uint32_t r = 0; r < MAX_PEERS; r++) pp.p[r] = r < world ? peer_roots[r] : nullptr;
+  for (uint32_t r = 0; r < world; r++)
+    if (!pp.p[r]) return ctx->fail_arg("null peer root");
+  uint32_t gl = 0;
+  while ((1u << gl) < world) gl++;
+  uint8_t *tree = ctx->d_scratch;  // heap order: the subtree roots are level gl
+  KL("gather_roots", launch_gather_roots(ctx->stream, pp, world, tree), 1);
+  KL("merkle_top", launch_merkle_top(ctx->stream, tree, 2 * (size_t)world, gl, 0, nullptr, 0, nullptr, nullptr, 0, 1), 1);
+  CU(cudaMemcpyAsync(root_out, tree + 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return FRIEDA_OK;
 }
 
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]) {

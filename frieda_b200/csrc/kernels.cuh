@@ -57,6 +57,25 @@ struct MerkleBottomParams {
 
 cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
                         uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
+// Packing of ONE blob whose bytes lie in `world` slices of slice_len bytes (a multiple of 16) behind
+// separate device pointers (peer-mapped memory of the other GPUs): read in place over NVLink.
+constexpr uint32_t MAX_PEERS = 64;
+struct PeerPtrs {
+  const uint8_t *p[MAX_PEERS];
+};
+cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t world, uint32_t rank, size_t slice_len,
+                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
+// tree slot (world + r) <- 32 bytes at roots.p[r]  (the leaves of the top tree of a split commit)
+cudaError_t launch_gather_roots(cudaStream_t st, const PeerPtrs &roots, uint32_t world, uint8_t *tree);
+// Barrier between the GPUs of a split commit, on the stream: every rank stores `epoch` into word
+// (channel * 64 + rank) of every peer's flag array and waits until all `world` words of its own array reach
+// it.  Stream order + the system-scope release/acquire make everything this rank wrote before the barrier
+// visible to kernels its peers launch after theirs.  *timeout_flag is set if a peer does not arrive in ~2 s.
+struct PeerFlags {
+  uint32_t *p[MAX_PEERS];
+};
+cudaError_t launch_peer_barrier(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
+                                uint32_t epoch, int *timeout_flag);
 cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw,
                             uint32_t *tw2);
 // Owned slice of the evaluation domain (bit-reversed order): [lo, lo + 2^log); lo is a

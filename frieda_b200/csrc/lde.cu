@@ -62,6 +62,147 @@ cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_
   return cudaGetLastError();
 }
 
+// One blob in `world` slices behind separate (peer-mapped) pointers.  1024 limbs are exactly 960 words =
+// 240 x 16 bytes, so a CTA stages one such chunk in shared memory with 240 coalesced 128-bit loads (slices are
+// multiples of 16 bytes: a 16-byte piece never straddles two) -- over NVLink that is the access pattern of a
+// bulk copy, where 4-byte loads reached a quarter of the link rate -- and cuts it into limbs from there.
+constexpr uint32_t PP_LIMBS = 4096, PP_BYTES = 15360;  // 4 x (1024 limbs = 3840 bytes) per CTA iteration
+__global__ void __launch_bounds__(256) pack_peers_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len,
+                                                          uint32_t len, uint32_t n_felts, uint32_t n_coef,
+                                                          uint32_t first_chunk, uint32_t *__restrict__ coef) {
+  __shared__ __align__(16) uint32_t w[PP_BYTES / 4 + 4];
+  const uint32_t t = threadIdx.x, n_chunks = n_coef / PP_LIMBS;
+  for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+    // every rank starts at its own slice, so the GPUs do not all read the same peer at the same time
+    uint32_t c = ci + first_chunk;
+    if (c >= n_chunks) c -= n_chunks;
+    const uint32_t k0 = c * PP_LIMBS;
+    if (k0 >= n_felts) {  // pure zero padding
+#pragma unroll
+      for (int i = 0; i < 4; i++) reinterpret_cast<uint4 *>(coef + k0)[t + 256 * i] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    uint4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {  // 960 pieces of 16 bytes: all loads of a thread are in flight together
+      const uint32_t piece = t + 256 * i;
+      v[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (piece < PP_BYTES / 16) {
+        const uint32_t byte = c * PP_BYTES + 16 * piece;  // < 2^31 + 16 KiB: inputs are below 2^31 bytes
+        if (byte < len) {
+          const uint32_t s = byte / slice_len;
+          const uint8_t *src = sl.p[s] + (byte - s * slice_len);
+          if (byte + 16 <= len) {
+            v[i] = *reinterpret_cast<const uint4 *>(src);
+          } else {
+            uint32_t q[4] = {0u, 0u, 0u, 0u};
+            for (uint32_t j = 0; byte + j < len; j++) q[j >> 2] |= (uint32_t)src[j] << (8 * (j & 3));
+            v[i] = make_uint4(q[0], q[1], q[2], q[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (t + 256 * i < PP_BYTES / 16) reinterpret_cast<uint4 *>(w)[t + 256 * i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t out[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t kl = 4 * (t + 256 * i) + j, bit = 30u * kl, wi = bit >> 5, off = bit & 31;
+        const uint32_t x = __funnelshift_r(w[wi], off > 2 ? w[wi + 1] : 0u, off) & 0x3fffffffu;
+        out[j] = k0 + kl < n_felts ? x : 0u;
+      }
+      reinterpret_cast<uint4 *>(coef + k0)[t + 256 * i] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    __syncthreads();
+  }
+}
+
+// polynomials below 4096 coefficients: one thread per limb
+__global__ void pack_peers_small_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len, uint32_t len,
+                                        uint32_t n_felts, uint32_t n_coef, uint32_t *__restrict__ coef) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_coef) return;
+  auto word = [&](uint32_t byte) -> uint32_t {
+    uint32_t v = 0;
+    for (uint32_t j = 0; j < 4 && byte + j < len; j++) {
+      const uint32_t b = byte + j, s = b / slice_len;
+      v |= (uint32_t)sl.p[s][b - s * slice_len] << (8 * j);
+    }
+    return v;
+  };
+  uint32_t val = 0;
+  if (k < n_felts) {
+    const uint32_t bit = 30u * k, byte = (bit >> 5) * 4, off = bit & 31;
+    val = __funnelshift_r(word(byte), off > 2 ? word(byte + 4) : 0u, off) & 0x3fffffffu;
+  }
+  coef[k] = val;
+}
+
+cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t world, uint32_t rank, size_t slice_len,
+                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef) {
+  if (world == 0 || world > MAX_PEERS || slice_len == 0 || (slice_len & 15) || len >= ((size_t)1 << 31) ||
+      slice_len >= ((size_t)1 << 31))
+    return cudaErrorInvalidValue;
+  for (uint32_t r = 0; r < world; r++)
+    if ((reinterpret_cast<uintptr_t>(slices.p[r]) & 15) != 0) return cudaErrorInvalidValue;
+  const uint32_t n_coef = 4u << poly_log;
+  if (n_coef < PP_LIMBS) {
+    pack_peers_small_kernel<<<(n_coef + 127) / 128, 128, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts,
+                                                                 n_coef, coef);
+    return cudaGetLastError();
+  }
+  uint32_t bx = n_coef / PP_LIMBS;
+  if (bx > 148 * 64) bx = 148 * 64;
+  // chunk holding the first byte of this rank's slice
+  const uint32_t first_chunk = (uint32_t)(((uint64_t)rank * slice_len / PP_BYTES) % (n_coef / PP_LIMBS));
+  pack_peers_kernel<<<bx, 256, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts, n_coef, first_chunk, coef);
+  return cudaGetLastError();
+}
+
+__global__ void gather_roots_kernel(const __grid_constant__ PeerPtrs roots, uint32_t world, uint8_t *tree) {
+  // 8 threads per root, 4 bytes each (the peer buffers are only guaranteed 4-byte aligned)
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, r = t >> 3, w = t & 7;
+  if (r >= world) return;
+  reinterpret_cast<uint32_t *>(tree)[(size_t)(world + r) * 8 + w] = reinterpret_cast<const uint32_t *>(roots.p[r])[w];
+}
+cudaError_t launch_gather_roots(cudaStream_t st, const PeerPtrs &roots, uint32_t world, uint8_t *tree) {
+  if (world == 0 || world > MAX_PEERS) return cudaErrorInvalidValue;
+  for (uint32_t r = 0; r < world; r++)
+    if ((reinterpret_cast<uintptr_t>(roots.p[r]) & 3) != 0) return cudaErrorInvalidValue;
+  gather_roots_kernel<<<(world * 8 + 127) / 128, 128, 0, st>>>(roots, world, tree);
+  return cudaGetLastError();
+}
+
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags flags, uint32_t world, uint32_t rank,
+                                    uint32_t channel, uint32_t epoch, int *timeout_flag) {
+  const uint32_t j = threadIdx.x;
+  if (j >= world) return;
+  __threadfence_system();
+  uint32_t *theirs = flags.p[j] + channel * MAX_PEERS + rank;  // my arrival, in peer j's array
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const uint32_t *mine = flags.p[rank] + channel * MAX_PEERS + j;  // peer j's arrival, in my array
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 1.9 GHz: a peer is gone; do not hang the GPU
+      atomicExch(timeout_flag, 1);
+      break;
+    }
+  }
+}
+cudaError_t launch_peer_barrier(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
+                                uint32_t epoch, int *timeout_flag) {
+  if (world == 0 || world > MAX_PEERS || rank >= world || channel > 1) return cudaErrorInvalidValue;
+  peer_barrier_kernel<<<1, MAX_PEERS, 0, st>>>(flags, world, rank, channel, epoch, timeout_flag);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- twiddles
 // T (length 2^K): for level l = 0..K-1 the x-coordinates of the first half of half_odds(K-l),
 // bit-reversed; then a trailing 1 (stwo slow_precompute_twiddles).

@@ -6,8 +6,11 @@
   [r N/G, (r+1) N/G) of the evaluation domain = one Merkle subtree at depth g.  Each rank computes
   its subtree root from the whole input (frieda_commit_split_local), the 32-byte roots are
   all-gathered (NCCL over NVLink/NVSwitch when the tensors are CUDA tensors), and every rank hashes
-  the top g levels (frieda_merkle_combine).  The reference has no counterpart (it is a
-  single-threaded CPU path, src/commit.rs:11-23); the result is the same root.
+  the top g levels (frieda_merkle_combine).  With peer-mapped symmetric memory (the default on one
+  NVLink node) neither exchange is a separate collective: each rank uploads 1/G of the blob, the
+  packing kernel reads all G slices in place over NVLink and the combine kernel reads the G roots in
+  place (`commit_split_peers`; two stream-ordered barriers, one host synchronisation).  The reference
+  has no counterpart (it is a single-threaded CPU path, src/commit.rs:11-23); the result is the same root.
 """
 from __future__ import annotations
 
@@ -47,17 +50,90 @@ def slice_bounds(n_bytes: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n_bytes, lo + per)
 
 
+class _PeerState:
+    """Peer-mapped (symmetric) buffers of one process group on one context: every rank's input slice and
+    every rank's subtree root are readable from every GPU over NVLink / NVSwitch."""
+
+    def __init__(self, dev, group, slice_cap: int):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        self.cap = slice_cap
+        self.buf = symm_mem.empty(slice_cap, dtype=torch.uint8, device=dev)
+        self.h_in = symm_mem.rendezvous(self.buf, group=g)
+        self.roots = symm_mem.empty(64 * 32, dtype=torch.uint8, device=dev)
+        self.h_roots = symm_mem.rendezvous(self.roots, group=g)
+        # signal words of the library's own stream-ordered barriers (2 channels x 64 ranks), zero before first use
+        self.flags = symm_mem.empty(128, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.h_flags = symm_mem.rendezvous(self.flags, group=g)
+        self.h_flags.barrier(channel=0)
+        torch.cuda.current_stream(dev).synchronize()
+        self.epoch = 0
+
+
+_peer_states = {}
+_peer_memory_broken = False
+
+
+def release_peer_memory(ctx=None):
+    """Frees the symmetric buffers (of one context, or all).  Called by Context.close() and at interpreter exit,
+    before the streams they were used on disappear."""
+    for key in [k for k in _peer_states if ctx is None or k[0] == ctx.device]:
+        del _peer_states[key]
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_peer_memory)
+
+
+def _peer_state(ctx, group, slice_len: int):
+    """Collective (every rank of the group calls it with the same slice_len); grow-only."""
+    import torch
+    key = (ctx.device, id(group))
+    st = _peer_states.get(key)
+    if st is None or st.cap < slice_len:
+        cap = 1 << 20
+        while cap < slice_len:
+            cap <<= 1
+        st = _PeerState(torch.device("cuda", ctx.device), group, cap)
+        _peer_states[key] = st
+    return st
+
+
+def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: int, world: int, group=None,
+                       st=None) -> bytes:
+    """The split commit over peer memory: ONE library call, ordered on the context's stream with one host
+    synchronisation at the end (frieda_commit_split_peers): upload my slice -> barrier kernel -> pack straight
+    out of the peers' slices (the all-gather is the packing kernel's loads over NVLink) -> LDE + Merkle of my
+    subtree -> root into my symmetric slot -> barrier kernel -> combine kernel reads the peers' roots in place.
+    No NCCL call on the data path."""
+    per = slice_bounds(n_bytes, 0, world)[1]
+    if st is None:
+        st = _peer_state(ctx, group, per)
+    st.epoch += 1
+    return ctx.commit_split_peers(host, log_blowup_factor, rank, st.h_in.buffer_ptrs, per,
+                                  [int(p) + 32 * r for r, p in enumerate(st.h_roots.buffer_ptrs)],
+                                  st.h_flags.buffer_ptrs, st.epoch)
+
+
 def commit_split(ctx, data, log_blowup_factor: int, group=None, rank: Optional[int] = None,
-                 world: Optional[int] = None, sharded_upload: Optional[bool] = None) -> bytes:
+                 world: Optional[int] = None, sharded_upload: Optional[bool] = None,
+                 peer_memory: Optional[bool] = None) -> bytes:
     """commit() of ONE blob with the evaluation domain split across the ranks of `group`.
     Every rank passes the same `data`; every rank returns the same 32-byte root.
 
     sharded_upload (default: on when world > 1): each rank copies only its 1/world slice of the input
-    to its GPU over its own PCIe link and the slices are all-gathered over NVLink (NCCL), instead of
-    every rank uploading the whole blob."""
+    to its GPU over its own PCIe link instead of every rank uploading the whole blob.
+    peer_memory (default: tried first when sharded_upload is on): the slices and the subtree roots live in
+    peer-mapped symmetric memory and are read in place over NVLink by the packing and combine kernels
+    (`commit_split_peers`); otherwise the slices and the roots are all-gathered with NCCL."""
     import numpy as np
     import torch
     import torch.distributed as dist
+    global _peer_memory_broken
     distributed = dist.is_available() and dist.is_initialized()
     if world is None:
         world = dist.get_world_size(group) if distributed else 1
@@ -69,6 +145,22 @@ def commit_split(ctx, data, log_blowup_factor: int, group=None, rank: Optional[i
     sub = torch.zeros(32, dtype=torch.uint8, device=dev)
     if sharded_upload is None:
         sharded_upload = world > 1 and distributed
+    if sharded_upload and world > 1 and peer_memory is not False and (peer_memory or not _peer_memory_broken):
+        host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        host = host.reshape(-1).view(np.uint8)
+        st = None
+        try:
+            st = _peer_state(ctx, group, slice_bounds(host.size, 0, world)[1])
+        except (ImportError, RuntimeError, AttributeError) as e:
+            # symmetric memory unavailable (old torch, no P2P mapping): the allocation / rendezvous is collective
+            # and fails on every rank alike, so all of them take the NCCL path below
+            if peer_memory:
+                raise
+            _peer_memory_broken = True
+            import warnings
+            warnings.warn(f"peer-mapped split commit unavailable ({e}); using NCCL all-gathers")
+        if st is not None:
+            return commit_split_peers(ctx, host, host.size, log_blowup_factor, rank, world, group, st)
     if sharded_upload and world > 1:
         host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
         host = host.reshape(-1).view(np.uint8)

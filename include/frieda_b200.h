@@ -168,9 +168,33 @@ int frieda_commit_split_local(frieda_ctx *ctx, const uint8_t *data, size_t len, 
  * over its own PCIe link and the slices were all-gathered over NVLink). */
 int frieda_commit_split_local_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t log_blowup,
                                      uint32_t rank, uint32_t world, uint8_t *d_subroot_out);
+/* Same over peer-mapped memory (NVLink / NVSwitch), with no all-gather of the input: slice r of the blob
+ * (bytes [r * slice_len, (r + 1) * slice_len), slice_len a multiple of 16) lies at peer_slices[r], a
+ * 16-byte aligned device pointer that is valid on this context's device (this GPU's own slice, or a peer's
+ * symmetric / IPC-mapped buffer).  The packing kernel reads the slices where they lie.  ASYNCHRONOUS on the context's
+ * stream: no host synchronisation, so the caller can order it between stream-ordered barriers (uploads
+ * done before, roots visible after).  world <= 64. */
+int frieda_commit_split_local_peers(frieda_ctx *ctx, const uint8_t *const *peer_slices, uint32_t world,
+                                    size_t slice_len, size_t len, uint32_t log_blowup, uint32_t rank,
+                                    uint8_t *d_subroot_out);
+/* The whole split commit of rank `rank` as ONE call with the exchanges done by the library's own kernels over
+ * peer-mapped memory (no NCCL on the data path): upload this rank's slice (host bytes
+ * [rank * slice_len, ...)) into peer_slices[rank] -> barrier -> pack from all slices in place -> LDE + Merkle
+ * subtree -> root into peer_roots[rank] -> barrier -> combine reading peer_roots[*] in place -> root_out (host).
+ * peer_flags[r]: 128 u32 of zero-initialised peer-mapped memory per rank (the barriers' signal words);
+ * epoch: a counter that every rank increases by one per call, starting at 1.  One host synchronisation.
+ * Returns FRIEDA_ERR_CUDA with "peer barrier timed out" if a peer does not arrive within ~2 s. */
+int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
+                              uint32_t world, uint8_t *const *peer_slices, size_t slice_len,
+                              uint8_t *const *peer_roots, uint32_t *const *peer_flags, uint32_t epoch,
+                              uint8_t root_out[32]);
 /* Hashes the top log2(world) Merkle levels over the gathered subtree roots
  * (d_subroots = world * 32 bytes of device memory, rank order) into root_out (host). */
 int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t world, uint8_t root_out[32]);
+/* Same with subtree root r read in place from peer_roots[r] (32 bytes each, peer-mapped device pointers):
+ * the exchange step of the split commit as loads over NVLink inside the combine kernel. */
+int frieda_merkle_combine_peers(frieda_ctx *ctx, const uint8_t *const *peer_roots, uint32_t world,
+                                uint8_t root_out[32]);
 
 /* ---- erasure recovery (the reference's README promises sampling/recovery, its code has none) --
  * Any ONE of the 2^log_blowup coset blocks of the committed evaluation determines the data.  block_evals (host):

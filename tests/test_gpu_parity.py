@@ -527,6 +527,50 @@ def test_commit_split_virtual_ranks(ctx, torch_mod, n_bytes, blow, worlds):
         assert ctx.merkle_combine(subs.data_ptr(), world) == want, world
 
 
+@pytest.mark.parametrize("n_bytes,blow,worlds", [
+    (1 << 20, 2, (2, 8)), (131072, 4, (1, 4, 16)), (3000, 3, (2, 16)), (100003, 2, (4, 8)), (17, 3, (2,)),
+])
+def test_commit_split_peer_slices_virtual_ranks(ctx, torch_mod, n_bytes, blow, worlds):
+    # the peer-memory path on ONE GPU: every "peer" slice is a separate device buffer, the packing kernel reads the
+    # slices in place and the combine kernel reads each root where its rank left it (frieda_b200/parallel.py)
+    torch = torch_mod
+    from frieda_b200.parallel import slice_bounds
+    data = O.splitmix64_bytes(0x4652494544414236, n_bytes)
+    want = O.commit(data, blow)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr)
+    for world in worlds:
+        per = slice_bounds(n_bytes, 0, world)[1]
+        slices = []
+        for r in range(world):
+            lo, hi = slice_bounds(n_bytes, r, world)
+            buf = torch.full((per,), 0xA5, dtype=torch.uint8, device="cuda")  # bytes past `len` must not matter
+            if hi > lo:
+                buf[: hi - lo] = torch.frombuffer(bytearray(data[lo:hi]), dtype=torch.uint8).cuda()
+            slices.append(buf)
+        roots = [torch.zeros(32, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            ctx.commit_split_local_peers([b.data_ptr() for b in slices], per, n_bytes, blow, r, roots[r].data_ptr())
+        stream.synchronize()
+        assert ctx.merkle_combine_peers([t.data_ptr() for t in roots]) == want, world
+
+
+def test_commit_split_peers_single_rank(ctx, torch_mod):
+    # frieda_commit_split_peers with world = 1: upload, barrier kernels (trivially satisfied), pack from the
+    # slice, subtree, combine -- the one-call path the multi-GPU host logic uses
+    torch = torch_mod
+    data = O.splitmix64_bytes(0x4652494544414236, 300007)
+    per = (len(data) + 15) // 16 * 16
+    sl = torch.empty(per, dtype=torch.uint8, device="cuda")
+    roots = torch.zeros(64 * 32, dtype=torch.uint8, device="cuda")
+    flags = torch.zeros(128, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for epoch in (1, 2, 3):
+        got = ctx.commit_split_peers(data, 3, 0, [sl.data_ptr()], per, [roots.data_ptr()], [flags.data_ptr()], epoch)
+        assert got == O.commit(data, 3)
+    assert flags.cpu().tolist()[0] == 3 and flags.cpu().tolist()[64] == 3
+
+
 def test_commit_split_single_process_api(ctx):
     from frieda_b200.parallel import commit_split
     data = pattern(50000)
