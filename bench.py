@@ -432,7 +432,12 @@ def c5_split(ctx, torch, dist, distributed, rank, world, barrier):
     if distributed:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     per = float(dt.item()) / iters
-    return {"workload": "C5: one 64 MiB blob, blowup 2^2, commit split into per-GPU subtrees + all-gather of roots",
+    from frieda_b200 import parallel as _par
+    exchange = ("single GPU" if world == 1 else
+                "NCCL all-gathers (peer mapping unavailable)" if _par._peer_memory_broken else
+                "peer-mapped memory: slices and roots read in place over NVLink by the library's kernels")
+    return {"workload": "C5: one 64 MiB blob, blowup 2^2, commit split into per-GPU subtrees, subtree roots combined",
+            "exchange": exchange,
             "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "blobs_per_s": 1.0 / per,
             "input_gb_per_s": n_bytes / per / 1e9, "n_gpus": world, "scaling": "strong",
             "timing": "host wall clock around the synchronous call, max over ranks (H2D of the blob included)"}
