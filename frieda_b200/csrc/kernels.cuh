@@ -70,7 +70,7 @@ cudaError_t launch_gather_roots(cudaStream_t st, const PeerPtrs &roots, uint32_t
 // Barrier between the GPUs of a split commit, on the stream: every rank stores `epoch` into word
 // (channel * 64 + rank) of every peer's flag array and waits until all `world` words of its own array reach
 // it.  Stream order + the system-scope release/acquire make everything this rank wrote before the barrier
-// visible to kernels its peers launch after theirs.  *timeout_flag is set if a peer does not arrive in ~2 s.
+// visible to kernels its peers launch after theirs.  *timeout_flag is set if a peer does not arrive in ~20 s.
 struct PeerFlags {
   uint32_t *p[MAX_PEERS];
 };

@@ -183,7 +183,7 @@ int frieda_commit_split_local_peers(frieda_ctx *ctx, const uint8_t *const *peer_
  * subtree -> root into peer_roots[rank] -> barrier -> combine reading peer_roots[*] in place -> root_out (host).
  * peer_flags[r]: 128 u32 of zero-initialised peer-mapped memory per rank (the barriers' signal words);
  * epoch: a counter that every rank increases by one per call, starting at 1.  One host synchronisation.
- * Returns FRIEDA_ERR_CUDA with "peer barrier timed out" if a peer does not arrive within ~2 s. */
+ * Returns FRIEDA_ERR_CUDA with "peer barrier timed out" if a peer does not arrive within ~20 s. */
 int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,
                               uint32_t world, uint8_t *const *peer_slices, size_t slice_len,
                               uint8_t *const *peer_roots, uint32_t *const *peer_flags, uint32_t epoch,
