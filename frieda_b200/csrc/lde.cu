@@ -49,9 +49,27 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ b
   }
 }
 
+constexpr uint32_t PP_LIMBS = 4096, PP_BYTES = 15360;  // 4 x (1024 limbs = 3840 bytes) per CTA iteration
+__global__ void pack_peers_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len, uint32_t len, uint32_t n_felts,
+                                  uint32_t n_coef, uint32_t first_chunk, size_t blob_stride, uint32_t *__restrict__ coef_all);
+
 cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
                         uint32_t n_felts, uint32_t poly_log, uint32_t *coef) {
   uint32_t n_coef = 4u << poly_log;
+  // 16-byte aligned batches of at least 4096 coefficients: the staged 128-bit kernel (the whole blob is one "slice")
+  if (n_coef >= PP_LIMBS && len > 0 && len < ((size_t)1 << 31) && (reinterpret_cast<uintptr_t>(blobs) & 15) == 0 &&
+      (stride & 15) == 0) {
+    PeerPtrs one;
+    for (uint32_t r = 0; r < MAX_PEERS; r++) one.p[r] = blobs;
+    const uint32_t slice = (uint32_t)((len + 15) / 16 * 16);
+    for (size_t b0 = 0; b0 < n_blobs; b0 += 65535) {
+      size_t nb = n_blobs - b0 < 65535 ? n_blobs - b0 : 65535;
+      one.p[0] = blobs + b0 * stride;
+      pack_peers_kernel<<<dim3(n_coef / PP_LIMBS, (unsigned)nb), 256, 0, st>>>(one, slice, (uint32_t)len, n_felts, n_coef, 0,
+                                                                              stride, coef + b0 * n_coef);
+    }
+    return cudaGetLastError();
+  }
   uint32_t bx = (n_coef + 255) / 256;
   if (bx > 1024) bx = 1024;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 65535) {
@@ -66,12 +84,15 @@ cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_
 // 240 x 16 bytes, so a CTA stages one such chunk in shared memory with 240 coalesced 128-bit loads (slices are
 // multiples of 16 bytes: a 16-byte piece never straddles two) -- over NVLink that is the access pattern of a
 // bulk copy, where 4-byte loads reached a quarter of the link rate -- and cuts it into limbs from there.
-constexpr uint32_t PP_LIMBS = 4096, PP_BYTES = 15360;  // 4 x (1024 limbs = 3840 bytes) per CTA iteration
+// blockIdx.y = blob of a batch (blob_stride bytes apart behind every slice pointer; a split blob is a batch of one).
 __global__ void __launch_bounds__(256) pack_peers_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len,
                                                           uint32_t len, uint32_t n_felts, uint32_t n_coef,
-                                                          uint32_t first_chunk, uint32_t *__restrict__ coef) {
+                                                          uint32_t first_chunk, size_t blob_stride,
+                                                          uint32_t *__restrict__ coef_all) {
   __shared__ __align__(16) uint32_t w[PP_BYTES / 4 + 4];
   const uint32_t t = threadIdx.x, n_chunks = n_coef / PP_LIMBS;
+  const size_t in_off = (size_t)blockIdx.y * blob_stride;
+  uint32_t *__restrict__ coef = coef_all + (size_t)blockIdx.y * n_coef;
   for (uint32_t ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
     // every rank starts at its own slice, so the GPUs do not all read the same peer at the same time
     uint32_t c = ci + first_chunk;
@@ -91,7 +112,7 @@ __global__ void __launch_bounds__(256) pack_peers_kernel(const __grid_constant__
         const uint32_t byte = c * PP_BYTES + 16 * piece;  // < 2^31 + 16 KiB: inputs are below 2^31 bytes
         if (byte < len) {
           const uint32_t s = byte / slice_len;
-          const uint8_t *src = sl.p[s] + (byte - s * slice_len);
+          const uint8_t *src = sl.p[s] + in_off + (byte - s * slice_len);
           if (byte + 16 <= len) {
             v[i] = *reinterpret_cast<const uint4 *>(src);
           } else {
@@ -159,7 +180,7 @@ cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t 
   if (bx > 148 * 64) bx = 148 * 64;
   // chunk holding the first byte of this rank's slice
   const uint32_t first_chunk = (uint32_t)(((uint64_t)rank * slice_len / PP_BYTES) % (n_coef / PP_LIMBS));
-  pack_peers_kernel<<<bx, 256, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts, n_coef, first_chunk, coef);
+  pack_peers_kernel<<<bx, 256, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts, n_coef, first_chunk, 0, coef);
   return cudaGetLastError();
 }
 
