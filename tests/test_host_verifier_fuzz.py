@@ -92,3 +92,42 @@ def test_host_verifier_agrees_with_oracle_on_mutations(isa, tmp_path):
     # the mutations must exercise both failing outcomes, not only "reject"
     counts = eval(r.stdout.split("FUZZ_OK", 1)[1])
     assert counts["reject"] > 100 and counts["panic"] > 0 and counts["accept"] == 0, counts
+
+
+def test_deserializer_and_verifier_survive_corrupted_bytes(blob_bytes):
+    """Memory safety of the proof codec and the host verifier: corrupted serialisations either fail to parse
+    (FriedaError) or verify to accept / reject / reference panic -- never anything else."""
+    import frieda_b200 as F
+    from oracle import oracle as O
+    _, opr = O.prove(blob_bytes[:20000], 3, O.make_config(3, 0, 12, 4))
+    raw = opr.serialize()
+    assert F.verify_proof(F.Proof.deserialize(raw), 3)
+    rng = random.Random(1234)
+    parsed = rejected = 0
+    for k in range(600):
+        b = bytearray(raw)
+        kind = rng.randrange(5)
+        if kind == 0:      # flip bits anywhere (headers and counts included)
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        elif kind == 1:    # truncate
+            del b[rng.randrange(len(b)):]
+        elif kind == 2:    # overwrite a 4-byte word with an extreme value
+            i = rng.randrange(0, len(b) - 4)
+            b[i:i + 4] = rng.choice([b"\xff\xff\xff\xff", b"\x00\x00\x00\x00", b"\x00\x00\x00\x80", b"\xff\xff\xff\x7f"])
+        elif kind == 3:    # extend with junk
+            b += bytes(rng.randrange(256) for _ in range(rng.randrange(1, 64)))
+        else:              # splice a window from elsewhere
+            i, j, n = rng.randrange(len(b) - 64), rng.randrange(len(b) - 64), rng.randrange(1, 64)
+            b[i:i + n] = b[j:j + n]
+        try:
+            p = F.Proof.deserialize(bytes(b))
+        except F.FriedaError:
+            rejected += 1
+            continue
+        parsed += 1
+        try:
+            assert F.verify_proof(p, 3) in (True, False)
+        except F.ReferencePanic:
+            pass
+    assert parsed > 50 and rejected > 50, (parsed, rejected)
