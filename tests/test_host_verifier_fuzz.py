@@ -1,5 +1,6 @@
-"""The host verifier (csrc/verify.cpp: lockstep Merkle walks, 8-/16-way hashing, batched field work) against
-the oracle's verifier on randomly mutated proofs, at every host ISA level.  The outcome (accept / reject /
+"""The host verifier (csrc/verify.cpp: lockstep Merkle walks, 8-/16-way hashing, batched field work) and the GPU batch
+verifier's core (csrc/verify_core.cuh, executed on the host) against the oracle's verifier on randomly mutated proofs, at
+every host ISA level.  The outcome (accept / reject /
 reference panic) must agree mutation by mutation: the reference goes layer by layer and stops at the first
 error or panic (src/proof.rs:79-101), which the lockstep schedule has to reproduce."""
 import os
@@ -15,6 +16,7 @@ WORKER = r"""
 import random, sys
 sys.path.insert(0, %(root)r)
 import frieda_b200 as F
+from frieda_b200 import api
 from oracle import oracle as O
 
 def outcome(fn):
@@ -67,6 +69,9 @@ for case, (n, cfg, seed) in enumerate([(3000, (2, 1, 9, 4), 5), (20000, (3, 0, 1
         assert kf == ko
         a, b = outcome(lambda: F.verify_proof(fp, seed)), outcome(lambda: O.verify(op, seed))
         assert a == b, (case, k, kf, a, b)
+        # the GPU batch verifier's core (same __host__ __device__ code as the kernels), run on the host
+        c = {1: "accept", 0: "reject", api.ERR_PANIC: "panic"}.get(api.verify_core_host(fp, seed), "error")
+        assert c == a, (case, k, kf, a, c)
         counts[a] += 1
         # restore shrunk counters so the owners free what they allocated
         rf, ro = F.Proof.deserialize(raw).c, opr.c
