@@ -19,10 +19,12 @@
 namespace frieda {
 
 constexpr int MB_THREADS = 256;
-// 4 CTAs per SM (64 registers, 48 KiB of shared memory each).  Probed on B200: forcing 5 or 6 resident CTAs
-// (48 / 40 registers, 512-leaf chunks) is 1-2 % slower -- the ALU pipe, not occupancy, bounds these kernels
-// (profiles/r01_ncu_summary.md).
-constexpr int MB_MIN_BLOCKS = 4;
+// 4 CTAs per SM (64 registers, 48 KiB of shared memory each).  Probed on B200: 3 CTAs (85 registers) are 4 % slower,
+// 5 or 6 (48 / 40 registers, 512-leaf chunks) 1-2 % slower (profiles/r01_ncu_summary.md).
+#ifndef FRIEDA_MB_MIN_BLOCKS
+#define FRIEDA_MB_MIN_BLOCKS 4
+#endif
+constexpr int MB_MIN_BLOCKS = FRIEDA_MB_MIN_BLOCKS;  // -DFRIEDA_MB_MIN_BLOCKS=n via FRIEDA_NVCC_FLAGS for probes
 constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB + 16 KiB of shared memory
 
 struct alignas(16) Hash32 {
