@@ -1,0 +1,45 @@
+"""Two real ranks over NVLink (skipped on boxes with one GPU): the split commit through peer-mapped memory
+(frieda_commit_split_peers) and through the NCCL form must both give the oracle's root."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import frieda_b200 as F
+from frieda_b200 import parallel
+from oracle import oracle as O
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = F.Context(local)
+for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3)):
+    data = np.frombuffer(O.splitmix64_bytes(0x4652494544414236, n_bytes), dtype=np.uint8).copy()
+    want = O.commit(data.tobytes(), blow)
+    for peers in (False, True):
+        for _ in range(3):  # repeated calls reuse the symmetric buffers and advance the barrier epoch
+            assert parallel.commit_split(ctx, data, blow, peer_memory=peers) == want, (n_bytes, blow, peers)
+assert not parallel._peer_memory_broken
+ctx.close()
+dist.barrier(); dist.destroy_process_group()
+if rank == 0: print("MULTI_GPU_OK")
+"""
+
+
+@pytest.mark.gpu
+def test_commit_split_two_ranks_peer_memory_and_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
