@@ -98,8 +98,10 @@ constexpr GConst g_zero_msg(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 // ZERO_LEAF: the caller guarantees h == 0, t = f = 0 and m[4..15] == 0 (a Merkle leaf): columns 2 and 3 of
 // round 0's first half then see only constants and are folded at compile time (the opaque IMAD adds would
 // otherwise hide that from the compiler).
-template <uint32_t MASK, bool ZERO_LEAF = false>
-FR_HD void blake2s_compress_t(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0,
+// Msg: anything indexable by a compile-time word number (a register array, or an accessor that fetches the word
+// from shared memory where it is used, which keeps the 16 message words out of the register file).
+template <uint32_t MASK, bool ZERO_LEAF = false, class Msg = const uint32_t *>
+FR_HD void blake2s_compress_t(uint32_t h[8], const Msg &m, uint32_t t0, uint32_t t1, uint32_t f0,
                               uint32_t f1, uint32_t one) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   uint32_t v8 = FR_B2S_IV0, v9 = FR_B2S_IV1, v10 = FR_B2S_IV2, v11 = FR_B2S_IV3;
@@ -149,6 +151,13 @@ FR_HD void merkle_hash_leaf(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
 #pragma unroll
   for (int i = 0; i < 8; i++) out[i] = 0;
   blake2s_compress_t<0x000Fu, true>(out, m, 0, 0, 0, 0, one);
+}
+// Merkle inner node with the message behind an accessor (see blake2s_compress_t).
+template <class Msg>
+FR_HD void merkle_hash_node_msg(const Msg &m, uint32_t out[8], uint32_t one = 1u) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  blake2s_compress_t<0xFFFFu, false, Msg>(out, m, 0, 0, 0, 0, one);
 }
 // Merkle inner node: hash_node(Some((left, right)), []); m = left || right.
 FR_HD void merkle_hash_node(const uint32_t m[16], uint32_t out[8], uint32_t one = 1u) {
