@@ -14,20 +14,12 @@
 //   SRC_NODES        leaves are 2^log existing nodes of tree level src_level (middle pass)
 // then reduces `levels` tree levels in shared memory and writes the surviving tops (and, when
 // write_all, every level on the way) into the heap-ordered tree.
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace frieda {
 
 constexpr int MB_THREADS = 256;
-// 4 CTAs per SM (64 registers, 48 KiB of shared memory each).  Probed on B200: 3 CTAs (85 registers) are 4 % slower,
-// 5 or 6 (48 / 40 registers, 512-leaf chunks) 1-2 % slower (profiles/r01_ncu_summary.md).
-#ifndef FRIEDA_MB_MIN_BLOCKS
-#define FRIEDA_MB_MIN_BLOCKS 4
-#endif
-constexpr int MB_MIN_BLOCKS = FRIEDA_MB_MIN_BLOCKS;  // -DFRIEDA_MB_MIN_BLOCKS=n via FRIEDA_NVCC_FLAGS for probes
-constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB + 16 KiB of shared memory
+constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB of shared memory (levels are reduced in place)
 
 struct alignas(16) Hash32 {
   uint4 lo, hi;
@@ -54,86 +46,8 @@ __device__ __forceinline__ uint32_t circle_fold_itw(const uint32_t *iblk, size_t
   return (e == 1 || e == 2) ? m31_neg(v) : v;
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(MB_THREADS, MB_MIN_BLOCKS) merkle_bottom_kernel(const MerkleBottomParams p) {
-  __shared__ Hash32 sm_a[1u << MB_CHUNK_LOG_MAX];
-  __shared__ Hash32 sm_b[1u << (MB_CHUNK_LOG_MAX - 1)];
-  const size_t blob = blockIdx.y;
-  const uint32_t chunk = blockIdx.x;
-  const uint32_t n_chunk = 1u << p.chunk_log;
-  const size_t leaf0 = (size_t)chunk << p.chunk_log;
-  Hash32 *tree = reinterpret_cast<Hash32 *>(p.tree) + blob * p.tree_stride;
-
-  if (SRC == SRC_NODES) {
-    const Hash32 *src = tree + ((size_t)1 << p.src_level) + leaf0;
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) sm_a[j] = src[j];
-  } else {
-    const size_t n = (size_t)1 << p.log;
-    QM31Mat amat;  // multiplication by this blob's folding alpha as a 4x4 matrix (m31.cuh)
-    if (SRC == SRC_FOLD_CIRCLE || SRC == SRC_FOLD_LINE) amat = qm31_mat(p.alpha[blob * p.alpha_stride]);
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
-      const size_t i = leaf0 + j;
-      uint32_t c0, c1, c2, c3;
-      if (SRC == SRC_COLS) {
-        const uint32_t *s = p.src_cols + blob * p.src_stride + i;
-        c0 = __ldg(s);
-        c1 = __ldg(s + n);
-        c2 = __ldg(s + 2 * n);
-        c3 = __ldg(s + 3 * n);
-      } else {
-        const uint2 *s = reinterpret_cast<const uint2 *>(p.src_cols + blob * p.src_stride) + i;
-        uint2 e0 = __ldg(s), e1 = __ldg(s + n), e2 = __ldg(s + 2 * n), e3 = __ldg(s + 3 * n);
-        QM31 a = {{e0.x, e1.x, e2.x, e3.x}}, b = {{e0.y, e1.y, e2.y, e3.y}};
-        uint32_t itw = SRC == SRC_FOLD_CIRCLE ? circle_fold_itw(p.itw_blk, i) : __ldg(p.itw_blk + i);
-        QM31 f = fri_fold_pair_mat(a, b, itw, amat);
-        c0 = f.v[0];
-        c1 = f.v[1];
-        c2 = f.v[2];
-        c3 = f.v[3];
-        uint32_t *d = p.dst_cols + blob * p.dst_stride + i;
-        d[0] = c0;
-        d[n] = c1;
-        d[2 * n] = c2;
-        d[3 * n] = c3;
-      }
-      uint32_t h[8];
-      merkle_hash_leaf(c0, c1, c2, c3, h, p.one);
-      store_hash(&sm_a[j], h);
-      if (p.write_all) store_hash(tree + n + i, h);
-    }
-  }
-  __syncthreads();
-  // level-by-level reduction, ping-pong between the two shared buffers
-  Hash32 *cur = sm_a, *nxt = sm_b;
-  uint32_t cnt = n_chunk;
-  uint32_t level = (SRC == SRC_NODES ? p.src_level : p.log);
-  size_t idx0 = leaf0;
-  for (uint32_t l = 0; l < p.levels; l++) {
-    cnt >>= 1;
-    level -= 1;
-    idx0 >>= 1;
-    const bool top = (l + 1 == p.levels);
-    for (uint32_t j = threadIdx.x; j < cnt; j += MB_THREADS) {
-      uint32_t m[16], h[8];
-      load_pair(cur + 2 * j, m);
-      merkle_hash_node(m, h, p.one);
-      store_hash(&nxt[j], h);
-      if (p.write_all || top) store_hash(tree + ((size_t)1 << level) + idx0 + j, h);
-    }
-    __syncthreads();
-    Hash32 *t = cur;
-    cur = nxt;
-    nxt = t;
-  }
-  if (p.levels == 0 && !p.write_all && SRC != SRC_NODES) {
-    // no reduction requested: the leaves themselves are the tops
-    const size_t n = (size_t)1 << p.log;
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) tree[n + leaf0 + j] = sm_a[j];
-  }
-}
-
-// ---------------------------------------------------------------- variant 2: node messages read from shared memory
-// Same pass, but the 16 message words of a node compression are not loaded into registers: they are fetched
+// ---------------------------------------------------------------- the pass
+// The 16 message words of a node compression are not loaded into registers: they are fetched
 // from shared memory at the point of use (10 rounds x 16 words = 160 LDS per compression; the LSU pipe is idle in
 // these kernels), which frees ~16 registers and lets more CTAs stay resident.  The level buffer is a structure of
 // arrays split by node parity -- word s of node n at E/O[n & 1][s][n >> 1], the odd half shifted by 16 banks -- so
@@ -142,7 +56,7 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MIN_BLOCKS) merkle_bottom_kerne
 // Resident CTAs per SM (measured, one FRI-commit wave of 1024 blobs): leaves-from-columns 20.09 / 19.50 / 18.84 ms
 // at 4 / 5 / 6; the fold variants 11.1 / 10.3 / 10.6 ms (the fold's 4x4 matrix wants the registers).
 template <int SRC>
-struct Mb2Occupancy {
+struct MbOccupancy {
   static constexpr int min_blocks = SRC == SRC_COLS ? 6 : 5;
 };
 constexpr uint32_t MB2_HALF = 1u << (MB_CHUNK_LOG_MAX - 1);
@@ -160,7 +74,7 @@ __device__ __forceinline__ void mb2_put(uint32_t *sm, uint32_t node, const uint3
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(MB_THREADS, Mb2Occupancy<SRC>::min_blocks) merkle_bottom2_kernel(const MerkleBottomParams p) {
+__global__ void __launch_bounds__(MB_THREADS, MbOccupancy<SRC>::min_blocks) merkle_bottom_kernel(const MerkleBottomParams p) {
   __shared__ uint32_t sm[2 * 8 * MB2_HALF + 16];
   const size_t blob = blockIdx.y;
   const uint32_t chunk = blockIdx.x;
@@ -257,20 +171,6 @@ cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomPar
     q.tree += b0 * p.tree_stride * 32;
     if (q.alpha) q.alpha += b0 * p.alpha_stride;
     dim3 grid(chunks, (unsigned)nb);
-    static const int variant = [] {
-      const char *e = std::getenv("FRIEDA_MERKLE_VARIANT");
-      return e ? std::atoi(e) : 2;
-    }();
-    if (variant == 2) {
-      switch (src) {
-        case SRC_COLS: merkle_bottom2_kernel<SRC_COLS><<<grid, MB_THREADS, 0, st>>>(q); break;
-        case SRC_FOLD_CIRCLE: merkle_bottom2_kernel<SRC_FOLD_CIRCLE><<<grid, MB_THREADS, 0, st>>>(q); break;
-        case SRC_FOLD_LINE: merkle_bottom2_kernel<SRC_FOLD_LINE><<<grid, MB_THREADS, 0, st>>>(q); break;
-        case SRC_NODES: merkle_bottom2_kernel<SRC_NODES><<<grid, MB_THREADS, 0, st>>>(q); break;
-        default: return cudaErrorInvalidValue;
-      }
-      continue;
-    }
     switch (src) {
       case SRC_COLS: merkle_bottom_kernel<SRC_COLS><<<grid, MB_THREADS, 0, st>>>(q); break;
       case SRC_FOLD_CIRCLE: merkle_bottom_kernel<SRC_FOLD_CIRCLE><<<grid, MB_THREADS, 0, st>>>(q); break;
