@@ -223,3 +223,14 @@ def test_batch_verifier_core_other_shapes(case, golden):
     p = F.Proof.deserialize(pr.serialize())
     assert _core(p, g["seed"]) == 1
     assert _core(p, (g["seed"] or 0) + 1) == 0
+
+
+def test_peer_entry_points_reject_a_null_context():
+    # the split-commit entry points over peer memory (include/frieda_b200.h) validate before touching a device
+    import ctypes as C
+    L = F.load_library()
+    ptrs = (C.c_void_p * 2)(None, None)
+    out = (C.c_uint8 * 32)()
+    assert L.frieda_commit_split_local_peers(None, ptrs, 2, 16, 32, 2, 0, None) == api.ERR_ARG
+    assert L.frieda_merkle_combine_peers(None, ptrs, 2, out) == api.ERR_ARG
+    assert L.frieda_commit_split_peers(None, None, 0, 2, 0, 2, ptrs, 16, ptrs, ptrs, 1, out) == api.ERR_ARG
