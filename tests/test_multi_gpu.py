@@ -20,11 +20,13 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = F.Context(local)
 for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3)):
-    data = np.frombuffer(O.splitmix64_bytes(0x4652494544414236, n_bytes), dtype=np.uint8).copy()
-    want = O.commit(data.tobytes(), blow)
     for peers in (False, True):
-        for _ in range(3):  # repeated calls reuse the symmetric buffers and advance the barrier epoch
-            assert parallel.commit_split(ctx, data, blow, peer_memory=peers) == want, (n_bytes, blow, peers)
+        # repeated calls reuse the symmetric buffers and advance the barrier epoch; the CONTENT changes every call, so
+        # a peer reading a stale copy of another rank's slice or root would give a wrong root
+        for k in range(4):
+            data = np.frombuffer(O.splitmix64_bytes(0x4652494544414236 + 977 * k + n_bytes, n_bytes), dtype=np.uint8).copy()
+            want = O.commit(data.tobytes(), blow)
+            assert parallel.commit_split(ctx, data, blow, peer_memory=peers) == want, (n_bytes, blow, peers, k)
 assert not parallel._peer_memory_broken
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
