@@ -90,7 +90,7 @@ EXPORTS = [
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
     "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_verify_batch",
     "frieda_verify_batch_bytes",
-    "frieda_verify_core_host", "frieda_proof_free",
+    "frieda_verify_core_host", "frieda_proof_query_positions", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
@@ -138,6 +138,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_verify_batch": (C.c_int, [vp, C.POINTER(pp), sz, vp, C.POINTER(C.c_int)]),
         "frieda_verify_batch_bytes": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(C.c_int)]),
         "frieda_verify_core_host": (C.c_int, [pp, u64p]),
+        "frieda_proof_query_positions": (C.c_longlong, [pp, u64p, C.POINTER(C.c_uint32), sz]),
         "frieda_proof_free": (None, [pp]),
         "frieda_proof_clone": (pp, [pp]),
         "frieda_proof_serialize": (sz, [pp, vp, sz]),
@@ -532,6 +533,21 @@ def verify_proof(proof: Proof, seed: Optional[int]) -> bool:
     if rc < 0:
         raise FriedaError(rc, "verify failed")
     return bool(rc)
+
+
+def query_positions(proof: Proof, seed: Optional[int]):
+    """Sorted distinct positions (bit-reversed evaluation-domain indices) that `proof.evaluations` belong to; an empty
+    list when the transcript is rejected before the queries are drawn."""
+    L = load_library()
+    sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+    n = int(L.frieda_proof_query_positions(proof.ptr, sp, None, 0))
+    if n == ERR_PANIC:
+        raise ReferencePanic(ERR_PANIC, "reference panics on this proof")
+    if n < 0:
+        raise FriedaError(n, "frieda_proof_query_positions failed")
+    buf = (C.c_uint32 * max(n, 1))()
+    L.frieda_proof_query_positions(proof.ptr, sp, buf, n)
+    return [int(buf[i]) for i in range(n)]
 
 
 def verify_core_host(proof: Proof, seed: Optional[int]) -> int:

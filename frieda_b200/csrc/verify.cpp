@@ -306,7 +306,8 @@ QM31 line_poly_eval(const QM31 *coeffs, uint32_t log, const QM31 *doublings) {
   return qm31_add(l, qm31_mul(r, doublings[0]));
 }
 
-int verify_impl(const frieda_proof *pr, const uint64_t *seed) {
+// positions_out != nullptr: stop after the Fiat-Shamir replay and hand back the query positions (sorted, distinct).
+int verify_impl(const frieda_proof *pr, const uint64_t *seed, std::vector<uint32_t> *positions_out = nullptr) {
   const frieda_pcs_config &cfg = pr->pcs_config;
   Channel ch;
   channel_init(ch);
@@ -341,6 +342,10 @@ int verify_impl(const frieda_proof *pr, const uint64_t *seed) {
   // queries (src/proof.rs:96)
   if (cfg.n_queries == 0 || cfg.n_queries > (1u << 24)) throw PanicError{};
   std::vector<uint32_t> q = generate_queries(ch, D, cfg.n_queries);
+  if (positions_out) {
+    *positions_out = q;
+    return 1;
+  }
   // FriVerifier::decommit (src/proof.rs:98-100).  The field work of all layers runs first (it does not
   // depend on any hash), then the layers' Merkle multi-proofs are checked in lockstep so that every tree
   // level of every layer is one batch of independent compressions.  The reference goes layer by layer
@@ -447,6 +452,23 @@ int verify_impl(const frieda_proof *pr, const uint64_t *seed) {
 
 }  // namespace
 }  // namespace frieda
+
+extern "C" long long frieda_proof_query_positions(const frieda_proof *proof, const uint64_t *seed_or_null,
+                                                  uint32_t *positions_out, size_t cap) {
+  if (!proof) return FRIEDA_ERR_ARG;
+  try {
+    std::vector<uint32_t> q;
+    const int rc = frieda::verify_impl(proof, seed_or_null, &q);
+    if (rc != 1) return rc;  // 0: the transcript does not lead to queries (layer count, last layer, proof of work)
+    if (positions_out)
+      for (size_t i = 0; i < q.size() && i < cap; i++) positions_out[i] = q[i];
+    return (long long)q.size();
+  } catch (const frieda::PanicError &) {
+    return FRIEDA_ERR_PANIC;
+  } catch (const std::bad_alloc &) {
+    return FRIEDA_ERR_ALLOC;
+  }
+}
 
 extern "C" int frieda_verify(const frieda_proof *proof, const uint64_t *seed_or_null) {
   if (!proof) return FRIEDA_ERR_ARG;

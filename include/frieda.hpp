@@ -194,6 +194,17 @@ inline std::pair<Commitment, Proof> commit_and_generate_proof(const std::vector<
 inline Proof generate_proof(const std::vector<uint8_t> &data, std::optional<uint64_t> seed, PcsConfig pcs_config) {
   return commit_and_generate_proof(data, seed, pcs_config).second;
 }
+// The positions `proof.evaluations` belong to (ascending; the reference leaves them implicit): indices into the
+// bit-reversed evaluation domain, from a replay of the verifier's transcript.  Empty when the transcript is rejected.
+inline std::vector<uint32_t> query_positions(const Proof &proof, std::optional<uint64_t> seed) {
+  uint64_t s = seed.value_or(0);
+  long long n = frieda_proof_query_positions(proof.raw(), seed ? &s : nullptr, nullptr, 0);
+  if (n == FRIEDA_ERR_PANIC) throw Panic("called `Option::unwrap()` on a `None` value");
+  if (n < 0) throw Error((int)n, "query_positions failed");
+  std::vector<uint32_t> out((size_t)n);
+  frieda_proof_query_positions(proof.raw(), seed ? &s : nullptr, out.data(), out.size());
+  return out;
+}
 // Takes the proof by value like the reference; throws Panic where the reference panics
 // (too few evaluations, src/proof.rs:166-173).
 inline bool verify_proof(Proof proof, std::optional<uint64_t> seed) {

@@ -135,6 +135,14 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
  *      Returns 1 (valid), 0 (invalid) or FRIEDA_ERR_PANIC where the reference panics
  *      (too few `evaluations`, src/proof.rs:166-173). */
 int frieda_verify(const frieda_proof *proof, const uint64_t *seed_or_null);
+/* The positions `proof.evaluations` belong to (src/proof.rs:62-66 gathers them in ascending query order, the
+ * reference leaves them implicit): replays the Fiat-Shamir transcript of verify_proof (src/proof.rs:80-96) and
+ * writes the sorted distinct query positions (indices into the bit-reversed evaluation domain of size
+ * 2^(log_size_bound + log_blowup_factor)) to positions_out[0 .. min(count, cap)).  Returns the count, 0 when the
+ * transcript is rejected before the queries are drawn (layer count, last layer, proof of work), or a negative
+ * FRIEDA_ERR_*.  Host only; positions_out may be NULL to query the count. */
+long long frieda_proof_query_positions(const frieda_proof *proof, const uint64_t *seed_or_null, uint32_t *positions_out,
+                                       size_t cap);
 
 /* GPU batch verification: results[i] = 1 / 0 / FRIEDA_ERR_PANIC per proof, same semantics as
  * frieda_verify.  seeds_or_null: one seed per proof, or NULL when no proof was seeded. */

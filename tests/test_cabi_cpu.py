@@ -234,3 +234,16 @@ def test_peer_entry_points_reject_a_null_context():
     assert L.frieda_commit_split_local_peers(None, ptrs, 2, 16, 32, 2, 0, None) == api.ERR_ARG
     assert L.frieda_merkle_combine_peers(None, ptrs, 2, out) == api.ERR_ARG
     assert L.frieda_commit_split_peers(None, None, 0, 2, 0, 2, ptrs, 16, ptrs, ptrs, 1, out) == api.ERR_ARG
+
+
+def test_query_positions_match_the_oracle_transcript(blob_bytes):
+    # frieda_proof_query_positions replays the verifier's transcript: same positions as the prover drew (oracle trace)
+    for data, seed, cfg in ((blob_bytes, None, (4, 1, 20, 20)), (bytes(i % 256 for i in range(5000)), 9, (3, 0, 33, 6))):
+        t = O.trace(data, seed, O.make_config(*cfg), with_trees=False)
+        p = F.Proof.deserialize(t.proof_bytes)
+        pos = F.query_positions(p, seed)
+        assert pos == sorted(set(int(x) for x in t.queries)) and len(pos) == len(p.evaluations)
+        assert F.query_positions(p, 12345) != pos                  # another seed, another transcript
+        q = p.clone()
+        q.proof_of_work += 1
+        assert F.query_positions(q, seed) == []                    # proof of work rejected before the queries
