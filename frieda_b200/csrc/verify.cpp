@@ -161,28 +161,28 @@ struct MerkleWalk {
 
   MerkleWalk(const uint8_t *root_, uint32_t log_, const std::vector<uint32_t> *pos_, const std::vector<QM31> *values_,
              const frieda_layer_proof *lp_)
-      : root(root_), pos(pos_), values(values_), lp(lp_), k((int)log_), log(log_) {}
+      : root(root_), pos(pos_), values(values_), lp(lp_), k((int)log_), log(log_) {
+    // a level never has more nodes than the leaf level: no reallocation while jobs point into cur / leaves
+    prev.reserve(pos_->size() + 1);
+    cur.reserve(pos_->size() + 1);
+    leaves.reserve(pos_->size() + 1);
+  }
   bool active() const { return !failed && !done; }
 
   // One job per node of the current level.  `left`/`right` of a job point into prev (stable until
-  // advance()), the proof, or `leaves`; `out` into cur, whose storage is reserved up front.
-  struct Pending {
-    const void *left, *right;
-  };
-  std::vector<Pending> pend;
+  // advance()), the proof, or `leaves`; `out` into cur, whose storage was reserved up front.
   std::vector<std::array<uint32_t, 8>> leaves;  // leaf messages: 4 values + 4 zero words
 
   void prepare(std::vector<HashJob> &jobs) {
     cur.clear();
-    pend.clear();
     size_t pi = 0, hi = 0, ci = 0;
+    const size_t n_prev = prev.size();
     const size_t n_colq = (k == (int)log) ? pos->size() : 0;
-    if (!have_prev) leaves.reserve(n_colq);  // no reallocation while jobs point into it
     for (;;) {
       bool have = false;
       uint32_t node = 0;
-      if (pi < prev.size()) {
-        node = prev[pi].index / 2;
+      if (pi < n_prev) {
+        node = prev[pi].index >> 1;
         have = true;
       }
       if (ci < n_colq && (!have || (*pos)[ci] < node)) {
@@ -190,14 +190,11 @@ struct MerkleWalk {
         have = true;
       }
       if (!have) break;
-      while (pi < prev.size() && prev[pi].index / 2 == node) pi++;
-      Node out;
-      out.index = node;
-      Pending pd;
+      while (pi < n_prev && (prev[pi].index >> 1) == node) pi++;
+      const void *half[2];
       if (have_prev) {
-        const void *half[2];
         for (int s = 0; s < 2; s++) {
-          if (hi < prev.size() && prev[hi].index == 2 * node + s) {
+          if (hi < n_prev && prev[hi].index == 2 * node + s) {
             half[s] = prev[hi].h;
             hi++;
           } else {
@@ -208,7 +205,6 @@ struct MerkleWalk {
             half[s] = lp->hash_witness + 32 * (size_t)hw_used++;
           }
         }
-        pd = {half[0], half[1]};
         // column values below the leaf layer: none (n_columns_in_layer == 0)
         if (ci < n_colq && (*pos)[ci] == node) ci++;
       } else {
@@ -219,12 +215,13 @@ struct MerkleWalk {
         ci++;
         const QM31 &v = (*values)[val_used++];
         leaves.push_back({v.v[0], v.v[1], v.v[2], v.v[3], 0, 0, 0, 0});
-        pd = {leaves.back().data(), ZERO8};
+        half[0] = leaves.back().data();
+        half[1] = ZERO8;
       }
-      cur.push_back(out);
-      pend.push_back(pd);
+      cur.emplace_back();
+      cur.back().index = node;
+      jobs.push_back({half[0], half[1], cur.back().h});
     }
-    for (size_t i = 0; i < cur.size(); i++) jobs.push_back({pend[i].left, pend[i].right, cur[i].h});
   }
   void advance() {
     prev.swap(cur);
