@@ -56,4 +56,7 @@ extern "C" {
     pub fn frieda_verify_batch(ctx: *mut frieda_ctx, proofs: *const *const frieda_proof, n: usize,
                                seeds_or_null: *const u64, results: *mut c_int) -> c_int;
     pub fn frieda_proof_free(proof: *mut frieda_proof);
+    // beyond the reference API: the positions `proof.evaluations` belong to (count, or 0 / negative)
+    pub fn frieda_proof_query_positions(proof: *const frieda_proof, seed_or_null: *const u64, positions_out: *mut u32,
+                                        cap: usize) -> i64;
 }
