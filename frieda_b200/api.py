@@ -90,7 +90,7 @@ EXPORTS = [
     "frieda_commit_batch_device", "frieda_fri_n_inner_layers", "frieda_fri_commit_batch",
     "frieda_fri_commit_batch_device", "frieda_prove", "frieda_prove_batch", "frieda_verify", "frieda_verify_batch",
     "frieda_verify_batch_bytes",
-    "frieda_verify_core_host", "frieda_proof_query_positions", "frieda_proof_free",
+    "frieda_verify_core_host", "frieda_verify_core_host_bytes", "frieda_ctx_take_error", "frieda_proof_query_positions", "frieda_proof_free",
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
@@ -136,8 +136,10 @@ def load_library(build_if_missing: bool = True):
         "frieda_prove_batch": (C.c_int, [vp, vp, sz, sz, sz, vp, cfgp, vp, C.POINTER(pp)]),
         "frieda_verify": (C.c_int, [pp, u64p]),
         "frieda_verify_batch": (C.c_int, [vp, C.POINTER(pp), sz, vp, C.POINTER(C.c_int)]),
-        "frieda_verify_batch_bytes": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(C.c_int)]),
+        "frieda_verify_batch_bytes": (C.c_int, [vp, vp, sz, vp, sz, vp, C.POINTER(C.c_int)]),
         "frieda_verify_core_host": (C.c_int, [pp, u64p]),
+        "frieda_verify_core_host_bytes": (C.c_int, [vp, sz, u64p]),
+        "frieda_ctx_take_error": (C.c_int, [vp]),
         "frieda_proof_query_positions": (C.c_longlong, [pp, u64p, C.POINTER(C.c_uint32), sz]),
         "frieda_proof_free": (None, [pp]),
         "frieda_proof_clone": (pp, [pp]),
@@ -338,6 +340,11 @@ class Context:
             out[name] = (int(n), float(ms))
         return out
 
+    def take_error(self):
+        """Synchronises the stream and raises what the asynchronous *_device entry points could not report when they
+        returned (ReferencePanic for the reference's "invalid degree" assert); clears the pending error."""
+        self._check(self._L.frieda_ctx_take_error(self._h))
+
     def set_debug_keep(self, on: bool):
         self._check(self._L.frieda_ctx_set_debug_keep(self._h, int(on)))
 
@@ -433,12 +440,19 @@ class Context:
         blob = np.ascontiguousarray(blob, dtype=np.uint8)
         offs = np.ascontiguousarray(byte_offsets, dtype=np.uint64)
         n = len(offs) - 1
-        res = (C.c_int * n)()
+        if n < 0:
+            raise FriedaError(ERR_ARG, "byte_offsets needs n + 1 entries")
+        res = (C.c_int * max(n, 1))()
         sd = None
         if seeds is not None:
             sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
-        self._check(self._L.frieda_verify_batch_bytes(self._h, blob.ctypes.data, offs.ctypes.data, n,
+            if sd.shape != (n,):
+                raise FriedaError(ERR_ARG, f"{n} proofs but {sd.shape} seeds")
+        # the library checks every offset against blob.size (FRIEDA_ERR_ARG), so a bad offsets array cannot make
+        # the upload read past the host buffer
+        self._check(self._L.frieda_verify_batch_bytes(self._h, blob.ctypes.data, blob.size, offs.ctypes.data, n,
                                                       sd.ctypes.data if sd is not None else None, res))
+        res = res[:n]
         return [int(x) for x in res]
 
     # -- split blob ----------------------------------------------------------------
@@ -555,6 +569,14 @@ def verify_core_host(proof: Proof, seed: Optional[int]) -> int:
     L = load_library()
     sp = C.byref(C.c_uint64(seed)) if seed is not None else None
     return int(L.frieda_verify_core_host(proof.ptr, sp))
+
+
+def verify_core_host_bytes(data: bytes, seed: Optional[int]) -> int:
+    """Same over one serialised (untrusted) proof: the kernels' parser and both phases on the CPU, raw words in."""
+    L = load_library()
+    a = np.frombuffer(bytes(data) + b"\0" * (-len(data) % 4), dtype=np.uint8).copy()
+    sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+    return int(L.frieda_verify_core_host_bytes(a.ctypes.data, len(data), sp))
 
 
 # ---- module-level functions with the reference's names (default context on device 0) ----------

@@ -123,6 +123,9 @@ struct frieda_ctx {
   size_t arena_bytes = 0;
   // small result staging
   uint8_t *d_scratch = nullptr;  // 8 KiB: [0, 4 KiB) top-of-tree scratch (2 x 64 slots), then small flags
+  // "invalid degree" flag of the asynchronous *_device entry points: set by the tail kernel, read and cleared
+  // by frieda_ctx_take_error (the host-buffer entry points use a flag inside the wave's workspace instead)
+  int *d_async_err() const { return reinterpret_cast<int *>(d_scratch + 4096 + 64); }
   // grow-only buffers of the proof path: gathered witnesses on the device, pinned readback on the host
   uint8_t *d_gather = nullptr;
   size_t d_gather_bytes = 0;
@@ -509,7 +512,7 @@ int commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride
 
 // ---- FRI commit phase for one wave; leaves all state in the arena ------------------------
 int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_stride, const uint64_t *d_seeds,
-             int staged_buf = -1) {
+             int staged_buf = -1, int *error_flag = nullptr) {
   const Geom &g = w.g;
   int rc;
   if ((rc = lde_wave(ctx, w, d_in, d_stride, staged_buf))) return rc;
@@ -554,7 +557,7 @@ int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_strid
   tp.alpha = at<QM31>(ctx, w.o_alpha);
   tp.alpha_stride = g.n_layers;
   tp.last_poly = at<QM31>(ctx, w.o_last);
-  tp.error_flag = at<int>(ctx, w.o_err);
+  tp.error_flag = error_flag ? error_flag : at<int>(ctx, w.o_err);
   tp.tt = table(ctx);
   KL("fri_tail", launch_tail(ctx->stream, tp, w.B), 1);
   return FRIEDA_OK;
@@ -606,7 +609,8 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
     } else if (seeds) {
       d_seeds = seeds + b0;
     }
-    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds, device_io ? -1 : buf))) return rc;
+    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds, device_io ? -1 : buf, device_io ? ctx->d_async_err() : nullptr)))
+      return rc;
     CU(cudaMemcpyAsync(roots_out + b0 * g.n_layers * 32, at<uint8_t>(ctx, w.o_roots), nb * g.n_layers * 32, out_kind,
                        ctx->stream));
     CU(cudaMemcpyAsync(last_poly_out + (b0 << g.log_last), at<QM31>(ctx, w.o_last), (nb * sizeof(QM31)) << g.log_last,
@@ -915,7 +919,8 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_scratch, 8192)) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->d_scratch, 8192)) != cudaSuccess ||
+      (e = cudaMemset(ctx->d_scratch, 0, 8192)) != cudaSuccess) {
     g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e);
     cudaGetLastError();
     delete ctx;
@@ -981,6 +986,17 @@ void *frieda_ctx_stream(const frieda_ctx *ctx) { return ctx ? (void *)ctx->strea
 int frieda_ctx_set_debug_keep(frieda_ctx *ctx, int on) {
   if (!ctx) return FRIEDA_ERR_ARG;
   ctx->debug_keep = on != 0;
+  return FRIEDA_OK;
+}
+
+int frieda_ctx_take_error(frieda_ctx *ctx) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, ctx->d_async_err(), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_async_err(), 0, sizeof(int), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (flag) return ctx->fail_arg("reference panics: invalid degree (reported by an asynchronous *_device call)", FRIEDA_ERR_PANIC);
   return FRIEDA_OK;
 }
 
@@ -1088,7 +1104,7 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
 // call returns without synchronising the stream.
 static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
                                    uint32_t rank, uint32_t world, uint8_t *d_subroot_out, bool device_input,
-                                   const PeerPtrs *peers = nullptr, size_t slice_len = 0) {
+                                   const PeerPtrs *peers = nullptr, size_t slice_len = 0, bool prepare_only = false) {
   if (!ctx) return FRIEDA_ERR_ARG;
   if ((!data && !peers && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || rank >= world) return ctx->fail_arg("world must be a power of two > rank");
@@ -1114,6 +1130,7 @@ static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t 
   size_t o_tree = bp.take(slots * 32);
   if ((rc = ensure_arena(ctx, bp.off))) return rc;
   ctx->have_last = false;
+  if (prepare_only) return FRIEDA_OK;  // everything that can fail on this rank alone has been checked / allocated
   const uint8_t *d_in = data;
   if (!device_input && !peers) {
     uint8_t *stage = at<uint8_t>(ctx, o_in);
@@ -1184,14 +1201,28 @@ int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, 
     fl.p[r] = r < world ? peer_flags[r] : nullptr;
     if (r < world && (!sl.p[r] || !rt.p[r] || !fl.p[r])) return ctx->fail_arg("null peer pointer");
   }
+  // Geometry checks, twiddles and workspace BEFORE this rank touches shared state: a rank that fails here has
+  // neither overwritten its slice nor entered a barrier its peers would then wait ~20 s on.
+  int rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len,
+                                   /*prepare_only=*/true);
+  if (rc) return rc;
   int *d_timeout = reinterpret_cast<int *>(ctx->d_scratch + 4096);
   CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
   // my slice of the input, over my own PCIe link
   const size_t lo = std::min(len, (size_t)rank * slice_len), hi = std::min(len, lo + slice_len);
   if (hi > lo) CU(cudaMemcpyAsync(peer_slices[rank], data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
   KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 0, epoch, d_timeout), 1);
-  int rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len);
-  if (rc) return rc;
+  rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len);
+  if (rc) {
+    // a launch failed after the first barrier: still arrive at the second one so the peers fail fast on the
+    // root they read (this rank reports its own error) instead of spinning until the barrier's timeout
+    const std::string keep = ctx->err;
+    launch_peer_barrier(ctx->stream, fl, world, rank, 1, epoch, d_timeout);
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    ctx->err = keep;
+    return rc;
+  }
   KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 1, epoch, d_timeout), 1);
   uint32_t gl = 0;
   while ((1u << gl) < world) gl++;

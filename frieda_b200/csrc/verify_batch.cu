@@ -85,6 +85,32 @@ int frieda_verify_core_host(const frieda_proof *proof, const uint64_t *seed_or_n
   return verify_resolve(st);
 }
 
+// The same core over raw, untrusted words: what verify_phase_{a,b}_kernel run per proof, on the CPU.
+int frieda_verify_core_host_bytes(const uint8_t *bytes, size_t len, const uint64_t *seed_or_null) {
+  if (!bytes || (len & 3) || (reinterpret_cast<uintptr_t>(bytes) & 3) || len > 0xffffffffull * 4) return FRIEDA_ERR_ARG;
+  const uint32_t *words = reinterpret_cast<const uint32_t *>(bytes);
+  const uint32_t n_words = (uint32_t)(len / 4);
+  uint32_t max_q = 1, n_layers = V_MAX_LAYERS;
+  if (n_words > 10 && words[0] == 0x41445246u) {
+    if (words[5] == 0 && words[4] > 4096) return FRIEDA_ERR_ARG;
+    if (words[3] > 20 && words[3] < 32) return FRIEDA_ERR_ARG;
+    max_q = words[5] ? 1u : (words[4] ? words[4] : 1u);
+  }
+  const uint32_t max_pos = 2 * max_q;
+  std::vector<VNode> leaves((size_t)n_layers * max_pos);
+  std::vector<uint32_t> queries(max_q);
+  std::vector<QM31> evals(max_q), alphas(V_MAX_LAYERS);
+  VProofState st;
+  VGen gp = make_gen();
+  verify_phase_a(words, n_words, seed_or_null, gp, st, leaves.data(), max_pos, queries.data(), max_q, evals.data(),
+                 alphas.data());
+  for (uint32_t l = 0; l < st.n_layers; l++)
+    if (st.n_leaf[l])
+      st.merkle_ok[l] = verify_phase_b(words, n_words, st.layer_off[l], st.D - l, leaves.data() + (size_t)l * max_pos,
+                                       st.n_leaf[l]);
+  return verify_resolve(st);
+}
+
 }  // extern "C"
 
 // Common path: `words` = concatenated FRDA encodings (host memory, ideally pinned), offs = word offsets.
@@ -139,12 +165,14 @@ static int verify_batch_words(frieda_ctx *ctx, const uint32_t *words, const std:
   return FRIEDA_OK;
 }
 
-extern "C" int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
-                                         const uint64_t *seeds_or_null, int *results);
+extern "C" int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, size_t bytes_len,
+                                         const uint64_t *byte_offsets, size_t n, const uint64_t *seeds_or_null,
+                                         int *results);
 // Serialised proofs (frieda_proof_serialize encoding), proof i at bytes + byte_offsets[i] .. byte_offsets[i+1];
-// offsets must be multiples of 4.  This is what a light client holds after receiving proofs.
-int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
-                              const uint64_t *seeds_or_null, int *results) {
+// offsets must be multiples of 4 and end inside the buffer.  This is what a light client holds after receiving
+// proofs: every byte is untrusted, the offsets and bytes_len are the caller's.
+int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, size_t bytes_len, const uint64_t *byte_offsets,
+                              size_t n, const uint64_t *seeds_or_null, int *results) {
   if (!ctx) return FRIEDA_ERR_ARG;
   if (!bytes || !byte_offsets || !results) return frieda_ctx_fail_arg(ctx, "null pointer");
   if (n == 0) return FRIEDA_OK;
@@ -154,8 +182,10 @@ int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint6
   uint32_t n_layers_max = 1, max_q = 1;
   for (size_t i = 0; i <= n; i++) {
     if (byte_offsets[i] & 3) return frieda_ctx_fail_arg(ctx, "proof offsets must be multiples of 4");
+    if (byte_offsets[i] > bytes_len) return frieda_ctx_fail_arg(ctx, "proof offset beyond the end of the byte buffer");
     offs[i] = byte_offsets[i] / 4;
     if (i && offs[i] < offs[i - 1]) return frieda_ctx_fail_arg(ctx, "proof offsets must be non-decreasing");
+    if (i && offs[i] - offs[i - 1] > 0xffffffffull) return frieda_ctx_fail_arg(ctx, "a proof longer than 16 GiB");
   }
   for (size_t i = 0; i < n; i++) {
     // header: magic, log_size_bound, log_blowup, log_last, n_queries (u64), pow_bits, pow (u64), n_evals, ...
@@ -163,14 +193,19 @@ int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint6
     const size_t len = offs[i + 1] - offs[i];
     uint32_t nq = 1, nl = 1;
     if (len > 10) {
-      nq = w[5] ? 4097u : w[4];
+      // capacity of this verifier (frieda_verify_batch returns the same error; frieda_verify has neither limit):
+      // a proof beyond it is UNSUPPORTED here, which must not be reported as "forged"
+      if (w[0] == 0x41445246u && w[5] == 0 && w[4] > 4096)
+        return frieda_ctx_fail_arg(ctx, "n_queries > 4096 is not supported by the batch verifier");
+      if (w[0] == 0x41445246u && w[3] > 20 && w[3] < 32)
+        return frieda_ctx_fail_arg(ctx, "log_last_layer_degree_bound > 20 is not supported by the batch verifier");
+      nq = w[5] ? 1u : w[4];  // n_queries >= 2^32: phase A reports the reference's behaviour without drawing
       size_t pos = 10 + 4 * (size_t)w[9];
       if (pos < len) {
         pos += 1 + 4 * (size_t)w[pos];
         if (pos < len) nl = w[pos];
       }
     }
-    if (nq > 4096) nq = 4096;  // phase A rejects proofs that do not fit the batch capacity
     if (nl > V_MAX_LAYERS) nl = V_MAX_LAYERS;
     max_q = nq > max_q ? nq : max_q;
     n_layers_max = nl > n_layers_max ? nl : n_layers_max;

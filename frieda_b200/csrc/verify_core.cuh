@@ -71,6 +71,16 @@ struct VReader {
     pos += k;
     return p;
   }
+  // `count` items of `words_per_item` words each.  The count is an untrusted word of the proof: the product is
+  // formed in 64 bits, so a count like 0x20000000 cannot wrap to a small `take` and pass the bounds check.
+  FR_HD const uint32_t *take_items(uint32_t count, uint32_t words_per_item) {
+    const uint64_t k = (uint64_t)count * words_per_item;
+    if (!ok || k > (uint64_t)(n - pos)) {
+      ok = false;
+      return w;
+    }
+    return take((uint32_t)k);
+  }
 };
 
 FR_HD QM31 v_q(const uint32_t *p) { return {{p[0], p[1], p[2], p[3]}}; }
@@ -102,9 +112,9 @@ FR_HD void verify_phase_a(const uint32_t *words, uint32_t n_words, const uint64_
   const uint32_t pow_bits = r.u32();
   const uint32_t pow_lo = r.u32(), pow_hi = r.u32();
   const uint32_t n_evals = r.u32();
-  const uint32_t *ev = r.take(4 * n_evals);
+  const uint32_t *ev = r.take_items(n_evals, 4);
   const uint32_t n_last = r.u32();
-  const uint32_t *last = r.take(4 * n_last);
+  const uint32_t *last = r.take_items(n_last, 4);
   const uint32_t n_layers = r.u32();
   if (!r.ok || n_layers == 0 || n_layers > V_MAX_LAYERS || n_layers > max_layers) return stop(0, 0, 0);
   st.n_layers = n_layers;
@@ -114,9 +124,9 @@ FR_HD void verify_phase_a(const uint32_t *words, uint32_t n_words, const uint64_
     st.layer_off[l] = r.pos;
     commit[l] = r.take(8);
     uint32_t nf = r.u32();
-    r.take(4 * nf);
+    r.take_items(nf, 4);
     uint32_t nh = r.u32();
-    r.take(8 * nh);
+    r.take_items(nh, 8);
     uint32_t nc = r.u32();
     r.take(nc);
     if (!r.ok) return stop(0, 0, 0);
@@ -174,7 +184,8 @@ FR_HD void verify_phase_a(const uint32_t *words, uint32_t n_words, const uint64_
     VReader lr{words, n_words, st.layer_off[l], true};
     lr.take(8);
     const uint32_t n_fri = lr.u32();
-    const uint32_t *fri = lr.take(4 * n_fri);
+    const uint32_t *fri = lr.take_items(n_fri, 4);
+    if (!lr.ok) return stop(0, l, 0);
     const uint32_t d = D - l;
     VNode *out = leaves + (size_t)l * max_pos;
     uint32_t n_out = 0, wit = 0, qe = 0, n_next = 0;
@@ -269,9 +280,9 @@ FR_HD int verify_phase_b(const uint32_t *words, uint32_t n_words, uint32_t layer
   VReader lr{words, n_words, layer_off, true};
   const uint32_t *root = lr.take(8);
   const uint32_t n_fri = lr.u32();
-  lr.take(4 * n_fri);
+  lr.take_items(n_fri, 4);
   const uint32_t n_hash = lr.u32();
-  const uint32_t *hw = lr.take(8 * n_hash);
+  const uint32_t *hw = lr.take_items(n_hash, 8);
   const uint32_t n_colw = lr.u32();
   if (!lr.ok || n_colw != 0 || n == 0) return 0;
   for (uint32_t j = 0; j < n; j++) {

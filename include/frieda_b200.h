@@ -94,6 +94,11 @@ int frieda_ctx_set_profiling(frieda_ctx *ctx, int on);
 long frieda_ctx_profile_read(frieda_ctx *ctx, char *out, size_t cap, int reset);
 /* The stream all of this context's kernels are launched on (a cudaStream_t). */
 void *frieda_ctx_stream(const frieda_ctx *ctx);
+/* The *_device entry points are asynchronous: where the reference would panic on the DATA (stwo's "invalid degree"
+ * assert inside FriProver::commit, src/proof.rs:52) they cannot say so when they return.  This call synchronises the
+ * stream and returns FRIEDA_ERR_PANIC if any *_device call since the last take hit that assert (FRIEDA_OK otherwise);
+ * it clears the pending error.  The host-buffer entry points report it themselves. */
+int frieda_ctx_take_error(frieda_ctx *ctx);
 
 /* ---- commit: replaces frieda::commit::commit (src/commit.rs:11-23) -------------------- */
 /* Host buffer in, 32-byte root out. */
@@ -149,11 +154,19 @@ long long frieda_proof_query_positions(const frieda_proof *proof, const uint64_t
 int frieda_verify_batch(frieda_ctx *ctx, const frieda_proof *const *proofs, size_t n, const uint64_t *seeds_or_null,
                         int *results);
 /* Same over SERIALISED proofs (frieda_proof_serialize encoding): proof i occupies bytes[byte_offsets[i] ..
- * byte_offsets[i+1]); `bytes` and all offsets 4-byte aligned, n + 1 offsets. */
-int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, const uint64_t *byte_offsets, size_t n,
-                              const uint64_t *seeds_or_null, int *results);
+ * byte_offsets[i+1]); `bytes` and all offsets 4-byte aligned, n + 1 non-decreasing offsets, none beyond bytes_len
+ * (FRIEDA_ERR_ARG otherwise).  The proof bytes themselves are untrusted: malformed proofs give results[i] = 0.
+ * Limits of the batch verifier (both entry points; frieda_verify has neither): n_queries <= 4096 and
+ * log_last_layer_degree_bound <= 20 -- a proof beyond them makes the CALL fail with FRIEDA_ERR_ARG rather than
+ * being reported as invalid. */
+int frieda_verify_batch_bytes(frieda_ctx *ctx, const uint8_t *bytes, size_t bytes_len, const uint64_t *byte_offsets,
+                              size_t n, const uint64_t *seeds_or_null, int *results);
 /* The batch verifier's core run on the host for ONE proof (self-check of the kernels' logic on CPU). */
 int frieda_verify_core_host(const frieda_proof *proof, const uint64_t *seed_or_null);
+/* Same over ONE serialised, untrusted proof (len a multiple of 4; `bytes` 4-byte aligned): exactly the parser and
+ * the two phases the kernels of frieda_verify_batch_bytes run, on the CPU.  1 / 0 / FRIEDA_ERR_PANIC, or
+ * FRIEDA_ERR_ARG beyond the batch verifier's capacity (see frieda_verify_batch_bytes). */
+int frieda_verify_core_host_bytes(const uint8_t *bytes, size_t len, const uint64_t *seed_or_null);
 
 /* ---- proof objects --------------------------------------------------------------------- */
 void frieda_proof_free(frieda_proof *proof);
