@@ -192,6 +192,32 @@ def run_reference(args):
     return 0
 
 
+def compressions_per_blob(blob_len, cfg):
+    """BLAKE2s compressions of commit + FRI layers for one blob, from the geometry: every committed layer
+    of 2^d points is a full binary tree (2^(d+1) - 1 compressions); layers d = D .. log_last + log_blowup + 1."""
+    n_felts = (blob_len * 8 + 29) // 30
+    poly_log = max((n_felts - 1).bit_length(), 2) - 2
+    D = poly_log + cfg[0]
+    last_log = cfg[1] + cfg[0]
+    return sum((2 << d) - 1 for d in range(last_log + 1, D + 1))
+
+
+def ncu_metrics():
+    """{kernel name as ctx profiling reports it: record} from the newest tracked profiles/r*_ncu_metrics.json."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.json")))
+    if not files:
+        return {}
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+    except Exception:
+        return {}
+    for rec in d.values():
+        rec["file"] = os.path.relpath(files[-1], ROOT)
+    return d
+
+
 def workload_config(args, blobs_per_step=None):
     return {
         "workload": "C3: batch of independent 128 KiB blobs, commit + FRI layers "
@@ -321,9 +347,12 @@ def main():
     alg_bytes = {"merkle_bottom_cols": n * (16 * N + 32 * (N >> 3)),
                  "fold_circle+merkle_bottom": n * (16 * N + 8 * N + 32 * (N >> 4)),
                  }.get(dom_name)
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_metrics.txt: 1.2417 GB read + 0.2957 GB written at 296 blobs per launch), per blob
-    ncu_traffic_per_blob = {"merkle_bottom_cols": (1.241675e9 + 0.295743744e9) / 296}.get(dom_name)
+    # DRAM traffic of the same kernel: dram__bytes_read.sum + dram__bytes_write.sum of the tracked `ncu --set full`
+    # capture (profiles/r*_ncu_metrics.json, written by scripts/ncu_summary.py --json with the git hash and the blobs
+    # per launch of the capture), scaled per blob
+    ncu_rec = ncu_metrics().get(dom_name)
+    ncu_traffic_per_blob = ((ncu_rec["dram_bytes_read"] + ncu_rec["dram_bytes_write"]) / ncu_rec["blobs_per_launch"]
+                            if ncu_rec else None)
     roofline = None
     if dom_name and dom_launches and alg_bytes:
         per_launch_s = dom_ms / 1e3 / dom_launches
@@ -333,15 +362,17 @@ def main():
                     "traffic": ncu_traffic_per_blob * n if ncu_traffic_per_blob else None,
                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                     "avg_launch_ms": dom_ms / dom_launches, "share_of_step": dom_ms / ms_dev,
+                    "traffic_source": ({k: ncu_rec[k] for k in ("file", "git", "blobs_per_launch")} if ncu_rec else None),
                     "note": "this kernel is INT ALU-pipe bound (BLAKE2s), not HBM bound: see int_roofline; the HBM "
                             "roof applies to the LDE / fold passes under `passes`. traffic = ncu DRAM bytes per blob "
-                            "at 296 blobs per launch scaled to this launch's blob count"}
+                            "of the tracked capture scaled to this launch's blob count"}
     kernels = {k: {"launches": v[0], "total_ms": round(v[1], 3), "share": round(v[1] / ms_dev, 4)}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])} if prof else {}
     # integer roofline: compressions per blob (SURVEY 8d, C2 commit+FRI = 1,048,498).  Each needs 648
     # xor/rotate instructions that only the ALU pipe executes, at 0.5 warp-instr/clk/SMSP (measured,
     # profiles/r01_pipe_rates_b200.txt): peak = 592 SMSPs x 32 lanes x clk / (648 x 2)
-    compress_per_blob = 1048498
+    compress_per_blob = compressions_per_blob(BLOB_LEN, CFG)
+    assert compress_per_blob == 1048498  # SURVEY 8(d), C2 commit + FRI
     hashes_per_s = value / world * compress_per_blob
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     int_peak = 148 * 4 * 32 * sm_mhz * 1e6 / (648 * 2)
@@ -365,10 +396,13 @@ def main():
     # free the big C3 buffers before the extra measurements
     del d_in, d_roots, d_last
     torch.cuda.empty_cache()
+    c5 = None
     if not args.no_extras:
-        # BASELINE config 5: ONE 64 MiB blob at blowup 2^2 split over all ranks (subtree roots all-gathered
-        # over NCCL); strong scaling.  Every rank takes part; timed end to end (H2D of the blob included).
-        line["c5_split"] = c5_split(ctx, torch, dist, distributed, rank, world, barrier)
+        # BASELINE config 5: ONE 64 MiB blob at blowup 2^2 split over all ranks (subtree roots exchanged over peer
+        # memory); strong scaling.  Every rank takes part; timed end to end (H2D of the blob included); the root is
+        # ASSERTED against the oracle's on every rank.
+        c5 = c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier)
+        line["c5_split"] = c5
     if rank == 0 and not args.no_extras:
         line["extras"] = extras(ctx, h_in.numpy(), cfg, torch)  # pinned host memory
     if rank == 0 and not args.no_passes:
@@ -391,6 +425,14 @@ def main():
                                 "sample": f"{n_threads * per_thread} blobs ({per_thread} per thread) in {dt:.1f} s; "
                                           f"1 thread: {v1:.3f} blobs/s",
                                 "single_thread_value": v1}
+    # compact copies of the two other BASELINE configs as the LAST keys, so that a tail of the line carries them
+    if rank == 0 and "extras" in line:
+        pc = line["extras"]["prove_c4_e2e"]
+        line["prove_c4"] = {"proofs_per_s": round(pc["blobs_per_s"], 1), "blobs": pc["blobs"], "n_queries": 64,
+                            "verify_ok": pc["proofs_verify"]}
+    if c5 is not None and "ms_per_blob" in c5:
+        line["c5"] = {"ms": round(c5["ms_per_blob"], 4), "n": world, "root_ok": c5["root_matches_oracle"],
+                      "exchange": c5["exchange_short"], "gb_per_s": round(c5["input_gb_per_s"], 2)}
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,7 +446,7 @@ def main():
 C5_ROOT = "7ab1d35e23dcb4b678524912e0fc0cdbcb6efaa34aa9f480f97f3138b3f0ee07"  # oracle, tests/golden/vectors.json
 
 
-def c5_split(ctx, torch, dist, distributed, rank, world, barrier):
+def c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier):
     import numpy as np
     from frieda_b200.parallel import commit_split, is_pow2
     if not is_pow2(world):
@@ -420,27 +462,37 @@ def c5_split(ctx, torch, dist, distributed, rank, world, barrier):
     blob = torch.from_numpy(z.astype("<u8").view(np.uint8)).pin_memory().numpy()
     root = commit_split(ctx, blob, 2, rank=rank, world=world)
     ok = root.hex() == C5_ROOT
-    for _ in range(2):
+    assert ok, f"rank {rank}/{world}: split commit root {root.hex()} != oracle root {C5_ROOT}"
+    for _ in range(3):
         commit_split(ctx, blob, 2, rank=rank, world=world)
-    iters = 5
+    iters = 8
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
+    ev0.record(stream)
     for _ in range(iters):
-        commit_split(ctx, blob, 2, rank=rank, world=world)
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        ok = ok and commit_split(ctx, blob, 2, rank=rank, world=world).hex() == C5_ROOT
+    ev1.record(stream)
+    stream.synchronize()
+    wall = time.perf_counter() - t0
+    assert ok, f"rank {rank}/{world}: a timed split commit returned a different root"
+    dt = torch.tensor([ev0.elapsed_time(ev1) / 1e3, wall], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    per = float(dt.item()) / iters
+    per = float(dt[0].item()) / iters
+    wall_per = float(dt[1].item()) / iters
     from frieda_b200 import parallel as _par
     exchange = ("single GPU" if world == 1 else
                 "NCCL all-gathers (peer mapping unavailable)" if _par._peer_memory_broken else
                 "peer-mapped memory: slices and roots read in place over NVLink by the library's kernels")
     return {"workload": "C5: one 64 MiB blob, blowup 2^2, commit split into per-GPU subtrees, subtree roots combined",
             "exchange": exchange,
-            "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "blobs_per_s": 1.0 / per,
+            "exchange_short": ("single" if world == 1 else "nccl" if _par._peer_memory_broken else "peer"),
+            "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "wall_ms_per_blob": wall_per * 1e3,
+            "blobs_per_s": 1.0 / per,
             "input_gb_per_s": n_bytes / per / 1e9, "n_gpus": world, "scaling": "strong",
-            "timing": "host wall clock around the synchronous call, max over ranks (H2D of the blob included)"}
+            "timing": "CUDA events on the context's stream around the synchronous calls, max over ranks (H2D of the "
+                      "blob included); wall_ms_per_blob = host clock around the same region"}
 
 
 def extras(ctx, host_np, cfg, torch):

@@ -83,6 +83,10 @@ def main():
         ("splitmix_c4_b0", O.splitmix64_bytes(0x4652494544410000, 131072), 0, (4, 0, 64, 20)),
         ("splitmix_c4_b7", O.splitmix64_bytes(0x4652494544410007, 131072), 7, (4, 0, 64, 20)),
         ("pattern_3000_b2_l2", pattern(3000), 5, (2, 2, 33, 8)),
+        # above one shared-memory LDE block (poly_log 17 / 20: strided LDE passes, extra Merkle middle passes)
+        ("splitmix_big_1MiB_b2", O.splitmix64_bytes(0x4652494544414236, 1 << 20), 11, (2, 0, 20, 12)),
+        ("splitmix_big_8MiB_b2", O.splitmix64_bytes(0x4652494544414236, 8 << 20), None, (2, 0, 20, 12)),
+        ("splitmix_big_1MiB_b4_l3", O.splitmix64_bytes(0x4652494544414237, 1 << 20), 3, (4, 3, 64, 10)),
     ]:
         c = O.make_config(*cfg)
         t = O.trace(data, seed, c, with_trees=False)

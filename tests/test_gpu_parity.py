@@ -169,6 +169,59 @@ def test_lde_pass_vs_oracle_fft(ctx, torch_mod, p, beta, nz_frac):
             assert first_diff(got[b, c], want) is None, (b, c, first_diff(got[b, c], want))
 
 
+def test_fold_pass_vs_oracle_c2_shape(ctx, torch_mod):
+    # frieda_pass_fold (the kernel behind bench.py's fold roofline figures) against the oracle's FRI layers at
+    # C2's shape: circle fold 2^18 -> 2^17 with alpha_0, then every line fold down to 2^5, two blobs per launch
+    torch = torch_mod
+    cfg = O.make_config(4, 0, 20, 20)
+    traces = [O.trace(O.splitmix64_bytes(0x4652494544410000 + b, 131072), b, cfg, stop_after_fri=True,
+                      with_trees=False) for b in range(2)]
+    n_layers = len(traces[0].layer_logs)
+    assert traces[0].layer_logs[0] == 18
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr)
+    for layer in range(n_layers):
+        lg = traces[0].layer_logs[layer]
+        src = np.stack([t.layer_columns[layer] for t in traces])                        # (2, 4, 2^lg)
+        want = np.stack([t.layer_columns[layer + 1] if layer + 1 < n_layers else t.last_eval for t in traces])
+        alpha = np.array([t.alphas[layer] for t in traces], dtype=np.uint32)           # (2, 4)
+        d_src = torch.from_numpy(src.view(np.int32)).cuda()
+        d_alpha = torch.from_numpy(alpha.view(np.int32)).cuda()
+        d_dst = torch.zeros((2, 4, 1 << (lg - 1)), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.pass_fold(d_src.data_ptr(), lg, layer == 0, 2, d_alpha.data_ptr(), d_dst.data_ptr())
+        stream.synchronize()
+        got = d_dst.cpu().numpy().view(np.uint32)
+        assert first_diff(got, want) is None, (layer, first_diff(got, want))
+
+
+@pytest.mark.parametrize("blob_len,stride,n,offset", [
+    (131072, 131072, 3, 0),      # C2 shape: the staged 128-bit kernel
+    (131072, 131088, 2, 0),      # padded stride, still 16-byte aligned
+    (131071, 131075, 3, 1),      # odd length, odd stride, misaligned base: the byte path
+    (1 << 20, 1 << 20, 1, 0),    # poly_log 17
+    (15361, 15376, 2, 0),        # one full staging chunk + 1 byte
+    (1000, 1000, 5, 0), (30, 30, 2, 0), (1, 1, 3, 0), (15, 19, 2, 3),
+])
+def test_pack_pass_vs_oracle(ctx, torch_mod, blob_len, stride, n, offset):
+    # frieda_pass_pack against bytes_to_felt_le / polynomial_from_bytes (src/utils.rs:10-33)
+    torch = torch_mod
+    rng = np.random.default_rng(blob_len + stride)
+    buf = rng.integers(0, 256, offset + n * stride + 16, dtype=np.uint8)
+    buf[offset + blob_len - 1::stride][:n] |= 0x80  # top bits of the last byte set: the last limb is partial
+    p = O.poly_log(blob_len)
+    d_buf = torch.from_numpy(buf).cuda()
+    d_coef = torch.full((n, 4 << p), -1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.pass_pack(d_buf.data_ptr() + offset, blob_len, stride, n, d_coef.data_ptr())
+    torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+    got = d_coef.cpu().numpy().view(np.uint32)
+    for b in range(n):
+        felts = O.bytes_to_felts(buf[offset + b * stride: offset + b * stride + blob_len].tobytes())
+        want = np.zeros(4 << p, dtype=np.uint32)
+        want[:len(felts)] = felts
+        assert first_diff(got[b], want) is None, (b, first_diff(got[b], want))
+
+
 def test_lde_linearity_full_size(ctx, torch_mod):
     # size-independent property at C2's full size: LDE(a + b) == LDE(a) + LDE(b) (mod P)
     torch = torch_mod
@@ -255,12 +308,21 @@ CASES = [
     ("e2e", 58, None, (4, 0, 20, 20)),
     ("pattern", 200, 3, (1, 0, 5, 3)),
     ("pattern", 40000, None, (3, 1, 17, 10)),
+    # above one shared-memory LDE block: poly_log 17 (one strided radix-16 pass) and poly_log 20 (two), D = 19 / 22
+    # (Merkle middle passes, kept-tree strides), and poly_log 17 at blowup 2^4 (D = 21) with an 8-coefficient last layer
+    ("splitmix", 1 << 20, 11, (2, 0, 20, 12)),
+    ("splitmix", 8 << 20, None, (2, 0, 20, 12)),
+    ("splitmix7", 1 << 20, 3, (4, 3, 64, 10)),
 ]
 
 
 def case_data(kind, n):
     if kind == "e2e":
         return b"This is the original data that needs to be made available."
+    if kind == "splitmix":
+        return O.splitmix64_bytes(0x4652494544414236, n)
+    if kind == "splitmix7":
+        return O.splitmix64_bytes(0x4652494544414237, n)
     return pattern(n)
 
 
@@ -338,6 +400,27 @@ def test_fri_commit_device_pointers(ctx, torch_mod):
     assert first_diff(d_last.cpu().numpy().view(np.uint32), last) is None
 
 
+def test_device_entry_point_reports_invalid_degree_through_take_error(ctx, torch_mod):
+    # stwo asserts "invalid degree" inside FriProver::commit; the asynchronous device entry point cannot report it when
+    # it returns, frieda_ctx_take_error does.  No input of the public API can trigger the assert (the evaluation IS the
+    # LDE of a polynomial), so this checks the plumbing: take_error synchronises the stream, returns OK after clean
+    # device calls, and can be called repeatedly.
+    torch = torch_mod
+    cfg = F.PcsConfig(4, 0, 20, 20)
+    blobs = np.stack([np.frombuffer(O.splitmix64_bytes(0x4652494544410000 + b, 4096), dtype=np.uint8) for b in range(3)])
+    L = 1 + ctx.n_inner_layers(4096, cfg)
+    d_in = torch.from_numpy(blobs).cuda()
+    d_roots = torch.zeros((3, L, 32), dtype=torch.uint8, device="cuda")
+    d_last = torch.zeros((3, 1, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.fri_commit_batch_ptr(d_in.data_ptr(), 4096, 4096, 3, None, cfg, d_roots.data_ptr(), d_last.data_ptr(),
+                             device=True)
+    ctx.take_error()  # synchronises: results are complete without any other sync
+    oroots, _ = O.fri_commit(blobs[2].tobytes(), None, O.make_config(4, 0, 20, 20))
+    assert [r.tobytes() for r in d_roots[2].cpu().numpy()] == oroots
+    ctx.take_error()
+
+
 def test_fri_reference_panic_shapes(ctx):
     with pytest.raises(F.ReferencePanic):
         ctx.fri_commit_batch(np.zeros((1, 2), dtype=np.uint8), None, F.PcsConfig(4, 0, 20, 4))
@@ -376,6 +459,8 @@ def test_proof_golden_vector_file(ctx, blob_bytes, golden):
             data = b"This is the original data that needs to be made available."
         elif name.startswith("splitmix_c4_b"):
             data = O.splitmix64_bytes(0x4652494544410000 + int(name.rsplit("b", 1)[1]), g["len"])
+        elif name.startswith("splitmix_big"):
+            data = O.splitmix64_bytes(0x4652494544414237 if name.endswith("l3") else 0x4652494544414236, g["len"])
         else:
             data = pattern(g["len"])
         root, pr = ctx.commit_and_generate_proof(data, g["seed"], F.PcsConfig(*g["cfg"]))
@@ -488,6 +573,34 @@ def test_prove_batch_c4_vs_oracle(ctx):
     for b in range(n):
         assert F.verify_proof(proofs[b], seeds[b])
         assert not F.verify_proof(proofs[b], seeds[b] + 1)
+
+
+def test_prove_batch_large_blobs_vs_oracle(ctx):
+    # 4 blobs of 1 MiB (poly_log 17, blowup 2^2): the strided-LDE -> FRI -> decommit combination, batched;
+    # every proof byte-exact against the oracle, then the same batch cut into waves of one blob
+    cfg = (2, 0, 24, 10)
+    n, blob_len = 4, 1 << 20
+    blobs = np.stack([np.frombuffer(O.splitmix64_bytes(0x4652494544414236 + b, blob_len), dtype=np.uint8)
+                      for b in range(n)])
+    seeds = [40 + b for b in range(n)]
+    want = [O.prove(blobs[b].tobytes(), seeds[b], O.make_config(*cfg)) for b in range(n)]
+    roots, proofs = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    for b in range(n):
+        assert roots[b].tobytes() == want[b][0], b
+        assert proofs[b].serialize() == want[b][1].serialize(), b
+        assert F.verify_proof(proofs[b], seeds[b]) and not F.verify_proof(proofs[b], seeds[b] + 1)
+    layer_roots, last = ctx.fri_commit_batch(blobs, seeds, F.PcsConfig(*cfg))
+    for b in range(n):
+        oroots, olast = O.fri_commit(blobs[b].tobytes(), seeds[b], O.make_config(*cfg))
+        assert [r.tobytes() for r in layer_roots[b]] == oroots, b
+        assert [tuple(int(x) for x in q) for q in last[b]] == olast, b
+    ctx.set_workspace_limit(400 << 20)  # one blob per wave
+    try:
+        roots2, proofs2 = ctx.prove_batch(blobs, seeds, F.PcsConfig(*cfg))
+    finally:
+        ctx.set_workspace_limit(0)
+    assert np.array_equal(roots, roots2)
+    assert [p.serialize() for p in proofs2] == [p.serialize() for p in proofs]
 
 
 def test_prove_batch_in_waves(ctx):
