@@ -56,6 +56,10 @@ extern "C" {
     pub fn frieda_verify_batch(ctx: *mut frieda_ctx, proofs: *const *const frieda_proof, n: usize,
                                seeds_or_null: *const u64, results: *mut c_int) -> c_int;
     pub fn frieda_proof_free(proof: *mut frieda_proof);
+    // wire formats: the library's flat encoding and the bincode-1.x layout of the serde-derived `Proof`
+    pub fn frieda_proof_serialize(proof: *const frieda_proof, out: *mut u8, cap: usize) -> usize;
+    pub fn frieda_proof_deserialize(bytes: *const u8, len: usize, proof_out: *mut *mut frieda_proof) -> c_int;
+    pub fn frieda_proof_serialize_bincode(proof: *const frieda_proof, out: *mut u8, cap: usize) -> usize;
     // beyond the reference API: the positions `proof.evaluations` belong to (count, or 0 / negative)
     pub fn frieda_proof_query_positions(proof: *const frieda_proof, seed_or_null: *const u64, positions_out: *mut u32,
                                         cap: usize) -> i64;
