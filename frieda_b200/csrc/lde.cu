@@ -13,6 +13,8 @@
 // hb using the twiddles whose index has hb as its high bits.  Each (blob, column, block) is one
 // CTA working in shared memory; HBM sees the coefficients once (L2 for re-reads) and the
 // evaluations once.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace frieda {
@@ -603,7 +605,22 @@ __device__ __forceinline__ void reg_stages_vec(uint32_t (&v)[N], int top, RowFn 
 constexpr int LDE_ROW = 36;            // padded row of 32 words
 constexpr int LDE_SUB = 32 * LDE_ROW;  // one 1024-point sub-FFT in shared memory
 
-template <int P, int THREADS, bool INPLACE>
+// Epilogue variants of lde_warp_kernel (round 2): how a lane's 32 finished points (one 128-byte row
+// of the warp's tile) reach HBM.
+//   BULK = false: rows re-read across lanes, 8 x (LDS.128 + STG.128) per lane, every store a coalesced 512 bytes;
+//   BULK = true : each lane hands its own row to the copy engine: fence.proxy.async + ONE cp.async.bulk
+//                 shared::cta -> global of 128 bytes (SASS: UBLKCP), no __syncwarp, no LDS / STG in the issue stream.
+//                 A warp's tile is never reused inside the kernel, so the only wait is before the CTA exits.
+__device__ __forceinline__ void bulk_store_row(uint32_t *gdst, const uint32_t *srow) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(srow))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_drain() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <int P, int THREADS, bool INPLACE, bool BULK = false>
 __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef, uint32_t *eval, uint32_t beta,
                                                            uint32_t n_felts, TwiddleTable tt, LdeRange rg,
                                                            uint32_t p_full, int vec_ok) {
@@ -709,12 +726,16 @@ __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef,
       uint32_t *roww = base + lane * LDE_ROW;
 #pragma unroll
       for (int m = 0; m < 32; m += 4) *reinterpret_cast<uint4 *>(roww + m) = make_uint4(v[m], v[m + 1], v[m + 2], v[m + 3]);
-      __syncwarp();
-      uint32_t *o = out + (sub << 10) + (lane << 2);
-      const uint32_t *src = base + (lane >> 3) * LDE_ROW + ((lane & 7) << 2);
+      if constexpr (BULK) {
+        bulk_store_row(out + idx0, roww);
+      } else {
+        __syncwarp();
+        uint32_t *o = out + (sub << 10) + (lane << 2);
+        const uint32_t *src = base + (lane >> 3) * LDE_ROW + ((lane & 7) << 2);
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-        *reinterpret_cast<uint4 *>(o + 128 * r) = *reinterpret_cast<const uint4 *>(src + 4 * r * LDE_ROW);
+        for (int r = 0; r < 8; r++)
+          *reinterpret_cast<uint4 *>(o + 128 * r) = *reinterpret_cast<const uint4 *>(src + 4 * r * LDE_ROW);
+      }
     } else {
 #pragma unroll
       for (int m = 0; m < 32; m++) {
@@ -723,6 +744,7 @@ __global__ void __launch_bounds__(THREADS) lde_warp_kernel(const uint32_t *coef,
       }
     }
   }
+  if constexpr (BULK) bulk_store_drain();  // the copy engine has read this CTA's shared memory
 }
 
 // poly_log 0: one coefficient per column; every layer is a replication.
@@ -773,32 +795,35 @@ __global__ void __launch_bounds__(256) lde_strided_r16_kernel(const uint32_t *__
   const uint32_t col = blockIdx.y;
   const size_t blob = blockIdx.z;
   const uint32_t rs = top - 4;  // log2 of the row stride
+  // indices are below 2^28 (D <= 28): 32-bit index arithmetic throughout
+  const uint32_t lo32 = (uint32_t)rg.lo, span = 1u << rg.log;
   uint32_t *ev = eval + ((blob * 4 + col) << rg.log) - rg.lo;  // local address = global index - rg.lo
-  const size_t rg_hi = rg.lo + ((size_t)1 << rg.log);
   const bool zero_col = (uint64_t)n_felts <= ((uint64_t)col << p);
   if (zero_col && !FIRST) return;
   // one thread per (sub-FFT, column position); sub-FFTs touching the owned range only
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t sub = (t >> rs) + (rg.lo >> top);
-  const size_t pos = t & (((size_t)1 << rs) - 1);
-  const size_t base = (sub << top) + pos;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sub = (t >> rs) + (lo32 >> top);
+  const uint32_t pos = t & ((1u << rs) - 1);
+  const uint32_t base = (sub << top) + pos;
+  const uint32_t rstep = 1u << rs;
   uint32_t v[16];
   if (FIRST) {
     if (zero_col) {
+      uint32_t idx = base;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        size_t idx = base + ((size_t)j << rs);
-        if (idx >= rg.lo && idx < rg_hi) ev[idx] = 0u;
-      }
+      for (int j = 0; j < 16; j++, idx += rstep)
+        if (idx - lo32 < span) ev[idx] = 0u;
       return;
     }
+    // top == p: the coefficient index is the index inside the block (the block index only selects twiddles)
     const uint32_t *c = coef + ((blob * 4 + col) << p);
-    const size_t mask = ((size_t)1 << p) - 1;
+    uint32_t ci = pos;
 #pragma unroll
-    for (int j = 0; j < 16; j++) v[j] = __ldg(c + ((base + ((size_t)j << rs)) & mask));
+    for (int j = 0; j < 16; j++, ci += rstep) v[j] = __ldg(c + ci);
   } else {
+    uint32_t idx = base;
 #pragma unroll
-    for (int j = 0; j < 16; j++) v[j] = ev[base + ((size_t)j << rs)];
+    for (int j = 0; j < 16; j++, idx += rstep) v[j] = ev[idx];
   }
 #pragma unroll
   for (int s = 0; s < 4; s++) {
@@ -813,10 +838,112 @@ __global__ void __launch_bounds__(256) lde_strided_r16_kernel(const uint32_t *__
       for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2);
     }
   }
+  uint32_t idx = base;
 #pragma unroll
-  for (int j = 0; j < 16; j++) {
-    size_t idx = base + ((size_t)j << rs);
-    if (!FIRST || (idx >= rg.lo && idx < rg_hi)) ev[idx] = v[j];
+  for (int j = 0; j < 16; j++, idx += rstep)
+    if (!FIRST || idx - lo32 < span) ev[idx] = v[j];
+}
+
+// Eight or nine layers in ONE sweep (round 2): top-1 .. top-R over 2^R rows that are 2^(top-R) apart, R = A + 4, as a
+// radix-2^A and a radix-16 register step with a transpose through shared memory in between.  A CTA owns a tile of
+// 2^R rows x 32 consecutive columns (32 / 64 KiB): every global access is a full 128-byte line per warp, as in
+// lde_strided_r16_kernel, but the evaluation array crosses HBM once for R layers instead of twice.
+//   step 1  thread (r, col): rows {16 j + r}, row-index bits R-1..4, layers top-1 .. top-A; twiddles CTA-uniform
+//   step 2  thread (h, col): rows {16 h + r}, row-index bits 3..0, layers top-A-1 .. top-R; twiddles per warp
+// The tile is stored [row][col]: both steps access it with lane = column, conflict-free without padding.
+// Every index is below 2^28 (D <= 28): 32-bit index arithmetic (the 64-bit form of the same code executed twice the
+// instructions, profiles/r02_ncu_summary.md).
+template <bool FIRST, int A>
+__global__ void __launch_bounds__(512) lde_strided_tile_kernel(const uint32_t *__restrict__ coef, uint32_t *eval,
+                                                               uint32_t p, uint32_t beta, uint32_t n_felts, uint32_t top,
+                                                               TwiddleTable tt, LdeRange rg) {
+  extern __shared__ uint32_t tile[];  // [2^R][32]
+  constexpr int R = A + 4, NA = 1 << A;
+  const uint32_t D = p + beta, K = D - 1;
+  const uint32_t col = blockIdx.y;
+  const size_t blob = blockIdx.z;
+  const uint32_t rs = top - R;  // log2 of the row stride
+  const uint32_t lo32 = (uint32_t)rg.lo, span = 1u << rg.log;
+  uint32_t *ev = eval + ((blob * 4 + col) << rg.log) - rg.lo;  // local address = global index - rg.lo
+  const bool zero_col = (uint64_t)n_felts <= ((uint64_t)col << p);
+  if (zero_col && !FIRST) return;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;  // 16 warps: w = r in step 1
+  const uint32_t cg_log = rs - 5;                                // column groups of 32 per sub-FFT
+  const uint32_t sub = (blockIdx.x >> cg_log) + (lo32 >> top);
+  const uint32_t col0 = ((blockIdx.x & ((1u << cg_log) - 1)) << 5) + lane;
+  const uint32_t base = (sub << top) + col0;
+  const uint32_t rstep = 16u << rs;
+  if (FIRST && zero_col) {
+    for (uint32_t h = w; h < (uint32_t)NA; h += 16) {
+      uint32_t idx = base + ((16 * h) << rs);
+#pragma unroll
+      for (int k = 0; k < 16; k++, idx += 1u << rs)
+        if (idx - lo32 < span) ev[idx] = 0u;
+    }
+    return;
+  }
+  {
+    // ---- step 1: rows 16 j + w, j = 0 .. 2^A - 1
+    uint32_t v[NA];
+    if (FIRST) {
+      // top == p: the block index `sub` only selects twiddles; the coefficient index is the index inside the block
+      const uint32_t *c = coef + ((blob * 4 + col) << p);
+      uint32_t ci = col0 + (w << rs);
+#pragma unroll
+      for (int j = 0; j < NA; j++, ci += rstep) v[j] = __ldg(c + ci);
+    } else {
+      uint32_t idx = base + (w << rs);
+#pragma unroll
+      for (int j = 0; j < NA; j++, idx += rstep) v[j] = ev[idx];
+    }
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+      const uint32_t i = top - 1 - s;
+      const uint32_t *tw = tt.blk2(1u << (K - i)) + (sub << s);  // index of row-group j: (sub << s) | (j >> (A - s))
+      const int half = NA >> (s + 1);
+#pragma unroll
+      for (int q = 0; q < (1 << s); q++) {
+        const uint32_t t2 = __ldg(tw + q);
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NA; j++) tile[(16 * j + w) * 32 + lane] = v[j];
+  }
+  __syncthreads();
+  // ---- step 2: rows 16 h + r, h = w (and w + 16 when A = 5)
+#pragma unroll 1
+  for (uint32_t h = w; h < (uint32_t)NA; h += 16) {
+    const uint32_t idx0 = base + ((16 * h) << rs);
+    // partial range (split blob, FIRST only): 16 rows that all lie outside the owned range have nothing to store
+    if (FIRST && span < (1u << top) && (idx0 + (15u << rs) < lo32 || idx0 >= lo32 + span)) continue;
+    uint32_t v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = tile[(16 * h + r) * 32 + lane];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const uint32_t i = top - A - 1 - s;
+      // index of row 16 h + r: (sub << (A + s)) | (h << s) | (r >> (4 - s)); 2^s consecutive words per warp
+      const uint32_t *tw = tt.blk2(1u << (K - i)) + (((sub << A) | h) << s);
+      const int half = 8 >> s;
+      uint32_t t2[8];
+      if (s == 0) t2[0] = __ldg(tw);
+      if (s == 1) { const uint2 q = __ldg(reinterpret_cast<const uint2 *>(tw)); t2[0] = q.x; t2[1] = q.y; }
+      if (s == 2) { const uint4 q = __ldg(reinterpret_cast<const uint4 *>(tw)); t2[0] = q.x; t2[1] = q.y; t2[2] = q.z; t2[3] = q.w; }
+      if (s == 3) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(tw)), q1 = __ldg(reinterpret_cast<const uint4 *>(tw) + 1);
+        t2[0] = q0.x; t2[1] = q0.y; t2[2] = q0.z; t2[3] = q0.w; t2[4] = q1.x; t2[5] = q1.y; t2[6] = q1.z; t2[7] = q1.w;
+      }
+#pragma unroll
+      for (int q = 0; q < (1 << s); q++)
+#pragma unroll
+        for (int k = 0; k < half; k++) bfly_t2(v[q * 2 * half + k], v[q * 2 * half + k + half], t2[q]);
+    }
+    uint32_t idx = idx0;
+#pragma unroll
+    for (int r = 0; r < 16; r++, idx += 1u << rs)
+      if (!FIRST || idx - lo32 < span) ev[idx] = v[r];
   }
 }
 
@@ -918,6 +1045,7 @@ cudaError_t launch_decode_block(cudaStream_t st, const uint32_t *block_evals, ui
   return cudaGetLastError();
 }
 
+constexpr bool LDE_BULK_DEFAULT = false;  // set from the measurement in profiles/r02_lde_probes.txt
 constexpr uint32_t LDE_SMEM_LOG_MAX = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
 
 cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, uint32_t p, uint32_t beta,
@@ -934,13 +1062,22 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     return cudaGetLastError();
   }
   static const bool attr_set = [] {  // blocks of 2^14 / 2^15 points need more than the default 48 KiB
-    cudaFuncSetAttribute(lde_warp_kernel<14, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
-    cudaFuncSetAttribute(lde_warp_kernel<14, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
-    cudaFuncSetAttribute(lde_warp_kernel<15, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
-    cudaFuncSetAttribute(lde_warp_kernel<15, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<14, 256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
+    cudaFuncSetAttribute(lde_warp_kernel<15, 512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * LDE_SUB * 4);
     return true;
   }();
   (void)attr_set;
+  // epilogue through the copy engine (cp.async.bulk) or through LDS/STG; FRIEDA_LDE_BULK=0/1 overrides (A/B probes)
+  static const bool bulk = [] {
+    const char *e = std::getenv("FRIEDA_LDE_BULK");
+    return e ? e[0] != '0' : LDE_BULK_DEFAULT;
+  }();
   const int vec_ok = (reinterpret_cast<uintptr_t>(eval) & 31) == 0;
   for (size_t b0 = 0; b0 < n_blobs; b0 += 32768) {
     size_t nb = n_blobs - b0 < 32768 ? n_blobs - b0 : 32768;
@@ -948,10 +1085,14 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
     uint32_t *ev = eval + b0 * ((size_t)4 << rg.log);
     if (p >= 10 && p <= LDE_SMEM_LOG_MAX) {
       dim3 grid(rg.log >= p ? 1u << (rg.log - p) : 1u, 4, (unsigned)nb);
-#define FR_LDE_WARP(PP, TT)                                                                                   \
-  case PP:                                                                                                    \
-    lde_warp_kernel<PP, TT, false><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, tt, rg, \
-                                                                                          p, vec_ok);          \
+#define FR_LDE_WARP(PP, TT)                                                                                           \
+  case PP:                                                                                                            \
+    if (bulk)                                                                                                         \
+      lde_warp_kernel<PP, TT, false, true><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, \
+                                                                                                 tt, rg, p, vec_ok);  \
+    else                                                                                                              \
+      lde_warp_kernel<PP, TT, false, false><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, \
+                                                                                                  tt, rg, p, vec_ok); \
     break;
       switch (p) {
         FR_LDE_WARP(10, 32) FR_LDE_WARP(11, 64) FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256)
@@ -971,15 +1112,45 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
       }
 #undef FR_LDE_CASE
     } else {
-      // m register-only radix-16 passes over layers p-1 .. c, then 2^c chunks in shared memory;
-      // c = p - 4m lies in 12..15.  After the first pass everything stays inside the owned range.
-      const uint32_t m = (p - LDE_SMEM_LOG_MAX + 3) / 4;
-      const uint32_t c = p - 4 * m;
-      if (rg.log < c || (rg.log < p && p - rg.log > 4)) return cudaErrorInvalidValue;
+      // Strided passes over the layers above the shared-memory chunks: tile sweeps of nine or eight layers (one HBM
+      // round trip each; nine when that leaves 2^14-point chunks, the size at which lde_warp_kernel keeps three CTAs
+      // per SM) while at least 2^12 points remain per chunk, otherwise a register-only radix-16 pass; then 2^c
+      // chunks in shared memory, c in 12..15.  After the first pass everything stays inside the owned range.
+      // FRIEDA_LDE_TILE=0 keeps to radix-16 passes (the round-1 schedule), =8 to eight-layer tiles (A/B probes).
+      static const int tile_mode = [] {
+        const char *e = std::getenv("FRIEDA_LDE_TILE");
+        return e ? std::atoi(e) : 9;
+      }();
+      static const bool tile_attr = [] {
+        cudaFuncSetAttribute(lde_strided_tile_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        cudaFuncSetAttribute(lde_strided_tile_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        return true;
+      }();
+      (void)tile_attr;
+      uint32_t c = p, n_pass = 0, radix_log[8];
+      while (c > LDE_SMEM_LOG_MAX) {
+        uint32_t r = 4;
+        if (tile_mode >= 9 && c - 14 == 9) r = 9;
+        else if (tile_mode >= 8 && c >= 20) r = 8;
+        radix_log[n_pass++] = r;
+        c -= r;
+      }
+      if (rg.log < c || (rg.log < p && p - rg.log > radix_log[0])) return cudaErrorInvalidValue;
       uint32_t top = p;
-      for (uint32_t pass = 0; pass < m; pass++, top -= 4) {
+      for (uint32_t pass = 0; pass < n_pass; top -= radix_log[pass], pass++) {
+        const size_t subs = rg.log >= top ? (size_t)1 << (rg.log - top) : 1;
+        const uint32_t r = radix_log[pass];
+        if (r >= 8) {
+          // CTAs = (sub-FFTs touching the range) x (2^(top-r) / 32 column groups); 512 threads
+          dim3 grid((unsigned)(subs << (top - r - 5)), 4, (unsigned)nb);
+          const size_t smem = (size_t)128 << r;
+          if (r == 8 && pass == 0) lde_strided_tile_kernel<true, 4><<<grid, 512, smem, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
+          if (r == 8 && pass != 0) lde_strided_tile_kernel<false, 4><<<grid, 512, smem, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
+          if (r == 9 && pass == 0) lde_strided_tile_kernel<true, 5><<<grid, 512, smem, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
+          if (r == 9 && pass != 0) lde_strided_tile_kernel<false, 5><<<grid, 512, smem, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
+          continue;
+        }
         // threads = (sub-FFTs touching the range) x 2^(top-4) column positions
-        size_t subs = rg.log >= top ? (size_t)1 << (rg.log - top) : 1;
         size_t threads = subs << (top - 4);
         dim3 grid((unsigned)(threads / 256), 4, (unsigned)nb);
         if (pass == 0)
@@ -988,10 +1159,14 @@ cudaError_t launch_lde(cudaStream_t st, const uint32_t *coef, uint32_t *eval, ui
           lde_strided_r16_kernel<false><<<grid, 256, 0, st>>>(cf, ev, p, beta, n_felts, top, tt, rg);
       }
       dim3 grid(1u << (rg.log - c), 4, (unsigned)nb);
-#define FR_LDE_WARP(PP, TT)                                                                                  \
-  case PP:                                                                                                   \
-    lde_warp_kernel<PP, TT, true><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, tt, rg, \
-                                                                                         p, vec_ok);          \
+#define FR_LDE_WARP(PP, TT)                                                                                          \
+  case PP:                                                                                                           \
+    if (bulk)                                                                                                        \
+      lde_warp_kernel<PP, TT, true, true><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, \
+                                                                                                tt, rg, p, vec_ok);  \
+    else                                                                                                             \
+      lde_warp_kernel<PP, TT, true, false><<<grid, TT, ((size_t)LDE_SUB * 4) << (PP - 10), st>>>(cf, ev, beta, n_felts, \
+                                                                                                 tt, rg, p, vec_ok); \
     break;
       switch (c) { FR_LDE_WARP(12, 128) FR_LDE_WARP(13, 256) FR_LDE_WARP(14, 256) FR_LDE_WARP(15, 512) }
 #undef FR_LDE_WARP

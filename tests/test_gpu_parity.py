@@ -147,11 +147,13 @@ def test_commit_batch_device_pointers(ctx, torch_mod):
                                             (14, 4, 0.53), (15, 2, 1.0), (16, 1, 0.55), (17, 2, 0.9),
                                             # zero-padded columns: the top layers of the column holding the last felt only replicate
                                             (14, 2, 0.2501), (14, 1, 0.26), (12, 2, 0.2503), (15, 1, 0.30), (13, 1, 0.5003),
-                                            (11, 2, 0.76), (10, 2, 0.27), (15, 1, 0.2500001)])
+                                            (11, 2, 0.76), (10, 2, 0.27), (15, 1, 0.2500001),
+                                            # radix-256 strided sweep (poly_log >= 20), alone and followed by radix-16
+                                            (20, 1, 0.8), (21, 2, 0.3), (22, 1, 1.0), (23, 1, 0.55), (24, 1, 0.26)])
 def test_lde_pass_vs_oracle_fft(ctx, torch_mod, p, beta, nz_frac):
     torch = torch_mod
     rng = np.random.default_rng(p * 31 + beta)
-    n_blobs = 2
+    n_blobs = 2 if p < 22 else 1
     n4 = 1 << p
     n_felts = max(1, int(4 * n4 * nz_frac))
     coef = np.zeros((n_blobs, 4 * n4), dtype=np.uint32)
