@@ -94,7 +94,7 @@ EXPORTS = [
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
-    "frieda_merkle_combine", "frieda_decode_block", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
+    "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
 
@@ -155,6 +155,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_commit_split_peers": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), sz,
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, u8p]),
         "frieda_decode_block": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, vp]),
+        "frieda_decode_blocks": (C.c_int, [vp, vp, vp, sz, sz, C.c_uint32, vp, C.POINTER(C.c_uint32)]),
         "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
         "frieda_pass_lde": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp]),
         "frieda_pass_merkle": (C.c_int, [vp, vp, C.c_uint32, sz, vp, vp]),
@@ -508,6 +509,18 @@ class Context:
         self._check(self._L.frieda_decode_block(self._h, ev.ctypes.data, length, log_blowup_factor, block,
                                                 out.ctypes.data))
         return out[:length].tobytes()
+
+    def decode_blocks(self, blocks: Sequence[np.ndarray], block_ids: Sequence[int], length: int,
+                      log_blowup_factor: int) -> Tuple[bytes, int]:
+        """Same from several whole coset blocks: returns (data, position in the list of the block it was decoded
+        from); corrupted blocks are skipped."""
+        ev = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.uint32) for b in blocks]))
+        ids = np.ascontiguousarray(np.asarray(block_ids, dtype=np.uint32))
+        out = np.zeros(max(length, 1), dtype=np.uint8)
+        used = C.c_uint32(0)
+        self._check(self._L.frieda_decode_blocks(self._h, ev.ctypes.data, ids.ctypes.data, len(ids), length,
+                                                 log_blowup_factor, out.ctypes.data, C.byref(used)))
+        return out[:length].tobytes(), int(used.value)
 
     # -- standalone passes / introspection ------------------------------------------
     def twiddles(self, k: int):

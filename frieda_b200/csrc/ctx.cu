@@ -1288,7 +1288,6 @@ int frieda_decode_block(frieda_ctx *ctx, const uint32_t *block_evals, size_t len
   int rc = make_geom(ctx, len, log_blowup, g);
   if (rc) return rc;
   if (g.D < 3) return ctx->fail_arg("domain too small to decode");
-  if (g.p > 15) return ctx->fail_arg("decode of polynomials above 2^15 coefficients per column is not supported");
   if (block >= (1u << log_blowup)) return ctx->fail_arg("block index out of range");
   if ((rc = ensure_twiddles(ctx, g.D - 1))) return rc;
   Bump bp;
@@ -1301,13 +1300,34 @@ int frieda_decode_block(frieda_ctx *ctx, const uint32_t *block_evals, size_t len
   KL("decode_block", launch_decode_block(ctx->stream, at<uint32_t>(ctx, o_ev), at<uint32_t>(ctx, o_coef), g.p, g.beta,
                                          block, table(ctx), len, g.n_felts, at<uint8_t>(ctx, o_out),
                                          at<int>(ctx, o_flag)),
-     2);
+     2 + (g.p > 15 ? g.p - 15 : 0));
   int flag = 0;
   if (len) CU(cudaMemcpyAsync(data_out, at<uint8_t>(ctx, o_out), len, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(&flag, at<int>(ctx, o_flag), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (flag) return ctx->fail_arg("the evaluations are not an encoding of `len` bytes");
   return FRIEDA_OK;
+}
+
+// Several coset blocks of one evaluation: the data is decoded from the first block in the list that is an encoding of
+// `len` bytes (a sampler that collected more than one block can hand over all of them; a corrupted block is skipped).
+int frieda_decode_blocks(frieda_ctx *ctx, const uint32_t *block_evals, const uint32_t *block_ids, size_t n_blocks,
+                         size_t len, uint32_t log_blowup, uint8_t *data_out, uint32_t *used_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!block_evals || !block_ids || n_blocks == 0) return ctx->fail_arg("no block to decode from");
+  Geom g;
+  int rc = make_geom(ctx, len, log_blowup, g);
+  if (rc) return rc;
+  const size_t words = (size_t)4 << g.p;
+  for (size_t k = 0; k < n_blocks; k++) {
+    rc = frieda_decode_block(ctx, block_evals + k * words, len, log_blowup, block_ids[k], data_out);
+    if (rc == FRIEDA_OK) {
+      if (used_out) *used_out = (uint32_t)k;
+      return FRIEDA_OK;
+    }
+    if (rc != FRIEDA_ERR_ARG) return rc;  // CUDA / allocation errors are not "this block is corrupted"
+  }
+  return ctx->fail_arg("none of the blocks is an encoding of `len` bytes");
 }
 
 // ---- standalone passes ------------------------------------------------------------------------

@@ -954,24 +954,26 @@ __global__ void __launch_bounds__(512) lde_strided_tile_kernel(const uint32_t *_
 // twiddles and scaling by 2^-p recovers the coefficients.  ibutterfly: (x, y) -> (x + y, (x - y) / t).
 // This is the decode side of the Reed-Solomon code the commit path encodes (the
 // reference's README describes sampling/recovery but its code has no counterpart).
+// Layers 0 .. c-1 of the inverse transform inside 2^c-point chunks (c = min(p, 15)); a chunk is one CTA in shared
+// memory.  The result is scaled by inv_n when the chunk is the whole block (p == c).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) lde_block_inverse_kernel(const uint32_t *__restrict__ block_evals,
-                                                                    uint32_t *__restrict__ coef, uint32_t p,
+                                                                    uint32_t *__restrict__ coef, uint32_t p, uint32_t c,
                                                                     uint32_t beta, uint32_t hb, uint32_t inv_n,
                                                                     TwiddleTable tt) {
   extern __shared__ uint32_t smi[];
-  const uint32_t col = blockIdx.x;
-  const uint32_t n4 = 1u << p;
+  const uint32_t col = blockIdx.y, ch = blockIdx.x;
+  const uint32_t n4 = 1u << c;
   const uint32_t D = p + beta, K = D - 1;
-  const uint32_t *src = block_evals + (size_t)col * n4;
+  const uint32_t *src = block_evals + ((size_t)col << p) + ((size_t)ch << c);
   for (uint32_t i = threadIdx.x; i < n4; i += THREADS) smi[i] = src[i];
   __syncthreads();
   const uint32_t half = n4 >> 1;
-  if (p >= 1) {
+  if (c >= 1) {
     // circle layer (pairs of neighbours), inverse twiddles [1/y, -1/y, -1/x, 1/x]
     const uint32_t *itw0 = tt.iblk(1u << (K - 1));
     for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
-      uint32_t h = (hb << (p - 1)) | bf;
+      uint32_t h = (hb << (p - 1)) | (ch << (c - 1)) | bf;
       uint32_t q = h >> 2, e = h & 3;
       uint32_t ix = __ldg(itw0 + 2 * q), iy = __ldg(itw0 + 2 * q + 1);
       uint32_t it = e == 0 ? iy : e == 1 ? m31_neg(iy) : e == 2 ? m31_neg(ix) : ix;
@@ -981,8 +983,9 @@ __global__ void __launch_bounds__(THREADS) lde_block_inverse_kernel(const uint32
     }
     __syncthreads();
   }
-  for (uint32_t i = 1; i < p; i++) {
-    const uint32_t *itw = tt.iblk(1u << (K - i)) + ((size_t)hb << (p - i - 1));
+  for (uint32_t i = 1; i < c; i++) {
+    // twiddle index of a butterfly = (index of its first point inside the evaluation domain) >> (i + 1)
+    const uint32_t *itw = tt.iblk(1u << (K - i)) + ((size_t)hb << (p - i - 1)) + ((size_t)ch << (c - i - 1));
     for (uint32_t bf = threadIdx.x; bf < half; bf += THREADS) {
       uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
       uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
@@ -993,8 +996,30 @@ __global__ void __launch_bounds__(THREADS) lde_block_inverse_kernel(const uint32
     }
     __syncthreads();
   }
-  uint32_t *dst = coef + (size_t)col * n4;
-  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) dst[i] = m31_mul(smi[i], inv_n);
+  uint32_t *dst = coef + ((size_t)col << p) + ((size_t)ch << c);
+  const uint32_t scale = p == c ? inv_n : 1u;
+  for (uint32_t i = threadIdx.x; i < n4; i += THREADS) dst[i] = m31_mul(smi[i], scale);
+}
+
+// One inverse layer i >= 15 over the whole block in HBM (polynomials above 2^15 coefficients per column): a thread
+// per butterfly, both accesses coalesced (the stride is at least 2^15).  `scale` (2^-p on the last layer, else 1)
+// multiplies both outputs.  Decoding is not on the commit path: one sweep per layer is good enough here.
+__global__ void __launch_bounds__(256) lde_inverse_layer_kernel(uint32_t *__restrict__ coef, uint32_t p, uint32_t i,
+                                                                uint32_t beta, uint32_t hb, uint32_t scale,
+                                                                TwiddleTable tt) {
+  const uint32_t D = p + beta, K = D - 1;
+  const uint32_t col = blockIdx.y;
+  uint32_t *v = coef + ((size_t)col << p);
+  const uint32_t *itw = tt.iblk(1u << (K - i)) + ((size_t)hb << (p - i - 1));
+  const uint32_t n_bf = 1u << (p - 1);
+  for (uint32_t bf = blockIdx.x * blockDim.x + threadIdx.x; bf < n_bf; bf += gridDim.x * blockDim.x) {
+    const uint32_t lo = bf & ((1u << i) - 1), hi = bf >> i;
+    const uint32_t a = (hi << (i + 1)) | lo, b = a + (1u << i);
+    const uint32_t it = __ldg(itw + hi);
+    const uint32_t x = v[a], y = v[b];
+    v[a] = m31_mul(m31_add(x, y), scale);
+    v[b] = m31_mul(m31_mul(m31_sub(x, y), it), scale);
+  }
 }
 
 // Inverse of pack_kernel: 30-bit limbs back to bytes.  flag[0] is set when the coefficients are not
@@ -1026,16 +1051,22 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict_
 cudaError_t launch_decode_block(cudaStream_t st, const uint32_t *block_evals, uint32_t *coef, uint32_t p,
                                 uint32_t beta, uint32_t hb, const TwiddleTable &tt, size_t len, uint32_t n_felts,
                                 uint8_t *out, int *flag) {
-  if (p > 15 || p + beta < 3) return cudaErrorInvalidValue;
+  if (p > 26 || p + beta < 3 || p + beta > 28) return cudaErrorInvalidValue;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(lde_block_inverse_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
     attr = true;
   }
   const uint32_t inv_n = m31_inv(1u << p);
-  lde_block_inverse_kernel<1024><<<4, 1024, (size_t)4 << p, st>>>(block_evals, coef, p, beta, hb, inv_n, tt);
+  const uint32_t c = p < 15 ? p : 15;
+  lde_block_inverse_kernel<1024><<<dim3(1u << (p - c), 4), 1024, (size_t)4 << c, st>>>(block_evals, coef, p, c, beta, hb,
+                                                                                      inv_n, tt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  for (uint32_t i = c; i < p; i++) {
+    lde_inverse_layer_kernel<<<dim3(2048, 4), 256, 0, st>>>(coef, p, i, beta, hb, i + 1 == p ? inv_n : 1u, tt);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   const uint32_t n_coef = 4u << p;
   size_t work = len > n_coef ? len : n_coef;
   unsigned bx = (unsigned)((work + 255) / 256);

@@ -217,13 +217,22 @@ int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t w
 int frieda_merkle_combine_peers(frieda_ctx *ctx, const uint8_t *const *peer_roots, uint32_t world,
                                 uint8_t root_out[32]);
 
-/* ---- erasure recovery (the reference's README promises sampling/recovery, its code has none) --
- * Any ONE of the 2^log_blowup coset blocks of the committed evaluation determines the data.  block_evals (host):
- * 4 columns x 2^poly_log u32 = entries [block * 2^poly_log, (block + 1) * 2^poly_log) of each evaluation column
- * (bit-reversed domain order, as produced by the commit path).  Writes the original `len` bytes to data_out;
- * FRIEDA_ERR_ARG if the block is not an encoding of `len` bytes.  poly_log <= 15 in this build. */
+/* ---- erasure recovery (the reference's README.md:56-70 promises sampling/recovery, its code has none) --
+ * The committed evaluation is a Reed-Solomon codeword of rate 2^-log_blowup made of 2^log_blowup coset blocks; ANY ONE
+ * whole block determines the data.  block_evals (host): 4 columns x 2^poly_log u32 = entries
+ * [block * 2^poly_log, (block + 1) * 2^poly_log) of each evaluation column (bit-reversed domain order, as produced
+ * by the commit path).  Writes the original `len` bytes to data_out; FRIEDA_ERR_ARG if the block is not an encoding
+ * of `len` bytes.  Any size the commit path accepts (inverse circle FFT: 2^15-point chunks in shared memory, one sweep
+ * per layer above that).
+ * NOT built: recovery from an arbitrary set of sampled POINTS (a general erasure decoder); a sampler has to collect at
+ * least one whole coset block. */
 int frieda_decode_block(frieda_ctx *ctx, const uint32_t *block_evals, size_t len, uint32_t log_blowup, uint32_t block,
                         uint8_t *data_out);
+/* Several blocks of the same evaluation, block k of the list (index block_ids[k]) at block_evals + k * 4 * 2^poly_log:
+ * decodes from the first one that is an encoding of `len` bytes (corrupted blocks are skipped); *used_out (may be
+ * NULL) receives its position in the list.  FRIEDA_ERR_ARG when none decodes. */
+int frieda_decode_blocks(frieda_ctx *ctx, const uint32_t *block_evals, const uint32_t *block_ids, size_t n_blocks,
+                         size_t len, uint32_t log_blowup, uint8_t *data_out, uint32_t *used_out);
 
 /* ---- standalone passes (bench.py's per-pass roofline; tests).  Device pointers. --------
  * LDE: d_coeffs = n * 4 * 2^poly_log u32 -> d_evals = n * 4 * 2^(poly_log+log_blowup) u32. */

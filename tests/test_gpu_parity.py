@@ -881,7 +881,9 @@ def test_error_paths_fail_loudly(ctx):
 
 
 # ------------------------------------------------------------------ encode -> erase -> decode
-@pytest.mark.parametrize("n_bytes,blow", [(58, 4), (1000, 2), (4097, 3), (65536, 1), (131072, 4), (262146, 4)])
+@pytest.mark.parametrize("n_bytes,blow", [(58, 4), (1000, 2), (4097, 3), (65536, 1), (131072, 4), (262146, 4),
+                                          # above one shared-memory chunk: poly_log 16, 17, 20 and config 5's 23
+                                          (300000, 3), (1 << 20, 2), (8 << 20, 1), (64 << 20, 2)])
 def test_encode_erase_decode_round_trip(ctx, torch_mod, blob_bytes, n_bytes, blow):
     # commit-path evaluations -> keep ONE of the 2^blowup coset blocks (erase the rest) -> recover the bytes
     torch = torch_mod
@@ -897,7 +899,8 @@ def test_encode_erase_decode_round_trip(ctx, torch_mod, blob_bytes, n_bytes, blo
     ctx.pass_lde(d_coef.data_ptr(), p, blow, 1, n_felts, d_eval.data_ptr())
     torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
     ev = d_eval.cpu().numpy().view(np.uint32).reshape(4, 1 << D)
-    for block in sorted({0, 1, (1 << blow) - 1, (1 << blow) // 2}):
+    blocks = sorted({0, 1, (1 << blow) - 1, (1 << blow) // 2}) if p < 22 else [(1 << blow) - 1]
+    for block in blocks:
         piece = ev[:, block << p: (block + 1) << p]
         assert ctx.decode_block(piece, len(data), blow, block) == data, (n_bytes, blow, block)
     # a corrupted block is not an encoding of `len` bytes (or decodes to different data)
@@ -907,3 +910,10 @@ def test_encode_erase_decode_round_trip(ctx, torch_mod, blob_bytes, n_bytes, blo
         assert ctx.decode_block(bad, len(data), blow, 0) != data
     except F.FriedaError as e:
         assert e.code == -4
+    if p < 22:
+        # several collected blocks, the first of them corrupted: decoded from the next one
+        last = (1 << blow) - 1
+        got, used = ctx.decode_blocks([bad, ev[:, last << p: (last + 1) << p]], [0, last], len(data), blow)
+        assert got == data and used == 1
+        with pytest.raises(F.FriedaError):
+            ctx.decode_blocks([bad], [0], len(data), blow)
