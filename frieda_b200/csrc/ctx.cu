@@ -68,11 +68,13 @@ struct Plan {
   size_t B = 0;
   uint32_t levels_cfg = 10;  // Merkle per-pass depth chosen for this call
   uint32_t nq = 0;  // n_queries (prove)
+  int small_cl = 0; // != 0: the latency path (fri_small.cu) with 2^small_cl leaves per CTA
   bool keep = false, prove = false, fri = false;
   size_t in_stride = 0;  // bytes between staged blobs
   size_t o_in = 0, o_in2 = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
   size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
   size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
+  size_t o_cnt = 0;
   size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_lvl = 0, o_offsets = 0, o_totals = 0,
          o_evals = 0;
   size_t total = 0;
@@ -108,6 +110,7 @@ struct frieda_ctx {
   size_t ws_limit = 0;
   uint32_t merkle_levels_big = 3;    // per-pass depth for large batches (env FRIEDA_MERKLE_LEVELS)
   uint32_t merkle_levels_small = 10; // per-pass depth when the grid would not fill the GPU anyway
+  bool small_path = true;            // latency path for a few blobs (env FRIEDA_SMALL_PATH=0 turns it off)
   uint32_t levels_for(size_t n_blobs, uint32_t d) const {
     // CTAs of the bottom pass; below ~4 waves of 148 SMs x 4 CTAs the launch count matters more
     size_t ctas = n_blobs << (d > 10 ? d - 10 : 0);
@@ -306,6 +309,7 @@ void layout(Plan &pl, size_t B, bool stage_input) {
     pl.o_last = bp.take(B * (sizeof(QM31) << g.log_last));
     pl.o_err = bp.take(256);
     pl.o_seeds = bp.take(B * 8);
+    pl.o_cnt = bp.take(B * g.n_layers * 4);
   }
   if (pl.prove) {
     pl.o_best = bp.take(B * 8);
@@ -418,6 +422,19 @@ int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channe
   return run_tree(ctx, src, mp, d, pl.levels_cfg, pl.keep, pl.B, roots, roots_stride, chan, alpha, g.n_layers);
 }
 
+// Few blobs: the FRI layers above the tail as one cooperative launch (fri_small.cu) when every CTA of it can be
+// resident.  The kept / truncated tree layout follows its chunk size.  FRIEDA_SMALL_PATH=0 disables it (A/B probes).
+void choose_small_path(frieda_ctx *ctx, Plan &pl, size_t n) {
+  pl.small_cl = 0;
+  if (!ctx->small_path || n > 8) return;
+  uint32_t n_big = 0;
+  while (n_big < pl.g.n_layers && layer_log(pl.g, n_big) > TAIL_LOG) n_big++;
+  const int cl = fri_small_chunk_log(pl.g.D, n_big, n);
+  if (!cl) return;
+  pl.small_cl = cl;
+  pl.levels_cfg = (uint32_t)cl;
+}
+
 CPoint half_initial_point(const Geom &g) { return host::point_from_index(half_odds_index(g.D - 1, 0)); }
 
 // pack + LDE of the wave's blobs (device pointer d_in, stride bytes) into cols[0]
@@ -517,14 +534,63 @@ int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_strid
   int rc;
   if ((rc = lde_wave(ctx, w, d_in, d_stride, staged_buf))) return rc;
   Channel *chan = at<Channel>(ctx, w.o_chan);
-  KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
   uint8_t *roots = at<uint8_t>(ctx, w.o_roots);
   const size_t roots_stride = (size_t)g.n_layers * 32;
   uint32_t layer = 0;
-  while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
-    int src = layer == 0 ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
-    if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
-    layer++;
+  if (w.small_cl) {
+    // latency path: channel initialisation and every layer above the tail in one cooperative launch
+    FriSmallParams sp;
+    std::memset(&sp, 0, sizeof sp);
+    while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
+      sp.cols[layer] = at<uint32_t>(ctx, w.o_cols[layer]);
+      sp.cols_stride[layer] = w.cols_stride[layer];
+      sp.tree[layer] = at<uint8_t>(ctx, w.o_tree[layer]);
+      sp.tree_stride[layer] = w.tree_stride[layer];
+      layer++;
+    }
+    sp.n_big = layer;
+    sp.D = g.D;
+    sp.n_blobs = (uint32_t)w.B;
+    sp.write_all = w.keep ? 1 : 0;
+    sp.seeds = d_seeds;
+    sp.roots = roots;
+    sp.roots_stride = roots_stride;
+    sp.chan = chan;
+    sp.alpha = at<QM31>(ctx, w.o_alpha);
+    sp.alpha_stride = g.n_layers;
+    sp.counters = at<uint32_t>(ctx, w.o_cnt);
+    static unsigned long long *dbg = nullptr;
+    if (std::getenv("FRIEDA_SMALL_TRACE") && !dbg) cudaMalloc(&dbg, 8 * (256 + 3 * 1024));
+    sp.trace = std::getenv("FRIEDA_SMALL_TRACE") ? dbg : nullptr;
+    sp.tt = table(ctx);
+    KL("fri_small", launch_fri_small(ctx->stream, sp, w.small_cl), 1);
+    if (sp.trace) {  // FRIEDA_SMALL_TRACE=1: per-layer stage times of CTA 0 on stderr (development aid)
+      {
+        static unsigned long long tt2[3 * 1024];
+        cudaMemcpyAsync(tt2, sp.trace + 256, sizeof tt2, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 256; i++) t0 = tt2[3 * i + 1] < t0 ? tt2[3 * i + 1] : t0;
+        for (int i = 0; i < 256; i += 8)
+          std::fprintf(stderr, "[cta %3d] sm %3llu start %6.2f end %6.2f\n", i, tt2[3 * i], (tt2[3 * i + 1] - t0) / 1e3,
+                       (tt2[3 * i + 2] - t0) / 1e3);
+      }
+      unsigned long long t[6 * 32];
+      CU(cudaMemcpyAsync(t, sp.trace, sizeof(unsigned long long) * 6 * sp.n_big, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      for (uint32_t l = 0; l < sp.n_big; l++)
+        std::fprintf(stderr, "[fri_small] layer %2u log %2u: leaves %6.2f  chunk %6.2f  wait %6.2f  top %6.2f  channel %6.2f us\n",
+                     l, layer_log(g, l), (t[6 * l + 1] - t[6 * l]) / 1e3, (t[6 * l + 2] - t[6 * l + 1]) / 1e3,
+                     (t[6 * l + 3] - t[6 * l + 2]) / 1e3, (t[6 * l + 4] - t[6 * l + 3]) / 1e3,
+                     (t[6 * l + 5] - t[6 * l + 4]) / 1e3);
+    }
+  } else {
+    KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
+    while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
+      int src = layer == 0 ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
+      if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
+      layer++;
+    }
   }
   const uint32_t s = layer;  // first layer handled by the tail (== n_layers: only the last evaluation)
   const uint32_t s_log = s < g.n_layers ? layer_log(g, s) : g.last_log;
@@ -577,8 +643,10 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
   pl.fri = true;
   pl.keep = ctx->debug_keep;
   pl.levels_cfg = ctx->levels_for(n, pl.g.D);
+  choose_small_path(ctx, pl, n);
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, !device_io, 0);
+  if (B < n) pl.small_cl = 0;  // (a few blobs that do not fit one wave: the throughput path handles waves)
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   const Geom &g = pl.g;
   const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -745,9 +813,11 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   pl.prove = true;
   pl.keep = true;
   pl.levels_cfg = ctx->levels_for(n, pl.g.D);
+  choose_small_path(ctx, pl, n);
   const uint32_t nq = (uint32_t)cfg->n_queries;
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, true, nq);
+  if (B < n) pl.small_cl = 0;
   tr.mark("plan");
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   tr.mark("arena");
@@ -926,6 +996,7 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
     delete ctx;
     return FRIEDA_ERR_CUDA;
   }
+  if (const char *ev = std::getenv("FRIEDA_SMALL_PATH")) ctx->small_path = ev[0] != '0';
   if (const char *ev = std::getenv("FRIEDA_MERKLE_LEVELS")) {
     int v = std::atoi(ev);
     if (v >= 1 && v <= 10) ctx->merkle_levels_big = (uint32_t)v;

@@ -86,41 +86,86 @@ cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits
 }
 
 // ---------------------------------------------------------------- queries
-// One thread per blob: mix_u64(nonce), then exactly n_queries draws of 4-byte chunks masked to
-// the domain, inserted into an ordered set (insertion sort + dedup).
-__global__ void queries_kernel(Channel *chan, const unsigned long long *nonce, uint32_t log_domain,
-                               uint32_t n_queries, uint32_t *queries, uint32_t *n_unique, size_t n) {
-  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
-  Channel c = chan[b];
-  channel_mix_u64(c, nonce[b]);  // src/proof.rs:59
-  uint32_t *q = queries + b * n_queries;
+// mix_u64(nonce), then exactly n_queries draws of 4-byte chunks masked to the domain, collected into an ordered set.
+// One CTA per blob: draw k of the channel hashes (digest, counter k), so the ceil(n_queries / 8) draws are
+// independent compressions spread over the threads; the values are then sorted (bitonic, shared memory) and
+// deduplicated with a scan.  (Round 1 did all of it in one thread per blob: 0.65 ms per 512 proofs.)
+constexpr int Q_THREADS = 128;
+constexpr uint32_t Q_MAX = 4096;  // n_queries limit of the proof path (ctx.cu)
+
+__global__ void __launch_bounds__(Q_THREADS) queries_kernel(Channel *chan, const unsigned long long *nonce,
+                                                            uint32_t log_domain, uint32_t n_queries, uint32_t *queries,
+                                                            uint32_t *n_unique) {
+  __shared__ uint32_t vals[Q_MAX];
+  __shared__ uint32_t part[Q_THREADS];
+  __shared__ Channel s_ch;
+  const size_t b = blockIdx.x;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    Channel c = chan[b];
+    channel_mix_u64(c, nonce[b]);  // src/proof.rs:59
+    s_ch = c;
+  }
+  __syncthreads();
   const uint32_t mask = log_domain >= 32 ? 0xffffffffu : ((1u << log_domain) - 1);
-  uint32_t cnt = 0, m = 0;
-  while (cnt < n_queries) {
+  const uint32_t n_draws = (n_queries + 7) / 8;
+  uint32_t n_pad = 1;
+  while (n_pad < n_queries) n_pad <<= 1;
+  for (uint32_t i = n_queries + tid; i < n_pad; i += Q_THREADS) vals[i] = 0xffffffffu;  // sorts behind every position
+  for (uint32_t k = tid; k < n_draws; k += Q_THREADS) {
+    Channel c = s_ch;
+    c.n_sent += k;  // draw k: H(digest || counter k)
     uint32_t w[8];
     channel_draw_random_words(c, w);
-    for (int i = 0; i < 8 && cnt < n_queries; i++, cnt++) {
-      uint32_t v = w[i] & mask;
-      // sorted insert, skipping duplicates
-      uint32_t lo = 0, hi = m;
-      while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (q[mid] < v) lo = mid + 1; else hi = mid;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (8 * k + i < n_queries) vals[8 * k + i] = w[i] & mask;
+  }
+  __syncthreads();
+  // bitonic sort of n_pad values, ascending
+  for (uint32_t size = 2; size <= n_pad; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = tid; t < (n_pad >> 1); t += Q_THREADS) {
+        const uint32_t lo = ((t / stride) * stride << 1) + (t % stride), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const uint32_t x = vals[lo], y = vals[hi];
+        if ((x > y) == up) {
+          vals[lo] = y;
+          vals[hi] = x;
+        }
       }
-      if (lo < m && q[lo] == v) continue;
-      for (uint32_t j = m; j > lo; j--) q[j] = q[j - 1];
-      q[lo] = v;
-      m++;
+      __syncthreads();
     }
   }
-  n_unique[b] = m;
-  chan[b] = c;
+  // keep the first of every run of equal values: per-thread contiguous piece, scan of the piece counts
+  const uint32_t per = (n_pad + Q_THREADS - 1) / Q_THREADS;
+  const uint32_t lo = tid * per, hi = lo + per < n_queries ? lo + per : n_queries;
+  uint32_t cnt = 0;
+  for (uint32_t i = lo; i < hi; i++) cnt += (i == 0 || vals[i] != vals[i - 1]) ? 1u : 0u;
+  part[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int t = 0; t < Q_THREADS; t++) {
+      const uint32_t c = part[t];
+      part[t] = run;
+      run += c;
+    }
+    n_unique[b] = run;
+    Channel c = s_ch;
+    c.n_sent += n_draws;
+    chan[b] = c;
+  }
+  __syncthreads();
+  uint32_t *q = queries + b * n_queries;
+  uint32_t at = part[tid];
+  for (uint32_t i = lo; i < hi; i++)
+    if (i == 0 || vals[i] != vals[i - 1]) q[at++] = vals[i];
 }
 cudaError_t launch_queries(cudaStream_t st, Channel *chan, const unsigned long long *nonce, uint32_t log_domain,
                            uint32_t n_queries, uint32_t *queries, uint32_t *n_unique, size_t n_blobs) {
-  queries_kernel<<<(unsigned)((n_blobs + 63) / 64), 64, 0, st>>>(chan, nonce, log_domain, n_queries, queries, n_unique,
-                                                                n_blobs);
+  if (n_queries == 0 || n_queries > Q_MAX) return cudaErrorInvalidValue;
+  queries_kernel<<<(unsigned)n_blobs, Q_THREADS, 0, st>>>(chan, nonce, log_domain, n_queries, queries, n_unique);
   return cudaGetLastError();
 }
 

@@ -129,6 +129,30 @@ constexpr uint32_t TAIL_LOG = 9;      // layers with log <= TAIL_LOG are finishe
 constexpr uint32_t TAIL_LAST_MAX = 9; // largest supported log_last + log_blowup
 cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs);
 
+// Latency path (fri_small.cu): layers 0 .. n_big-1 (those with more than 2^TAIL_LOG points) of a few blobs in ONE
+// cooperative launch, channel initialisation included; fold + fri_tail_kernel finish as usual.
+struct FriSmallParams {
+  uint32_t *cols[32];   // per layer: columns base (layer 0 read, layers >= 1 written)
+  size_t cols_stride[32];
+  uint8_t *tree[32];
+  size_t tree_stride[32];
+  uint32_t n_big, D, n_blobs;
+  int write_all;
+  const uint64_t *seeds;  // device, or nullptr
+  uint8_t *roots;         // [blob][n_layers][32]
+  size_t roots_stride;
+  Channel *chan;
+  QM31 *alpha;            // [blob][layer]
+  size_t alpha_stride;
+  uint32_t *counters;     // [n_big][n_blobs], zeroed by the launcher
+  unsigned long long *trace;  // development aid: 6 globaltimer stamps per layer from CTA 0 (or nullptr)
+  TwiddleTable tt;
+  uint32_t one;           // runtime 1 (blake2s.cuh); set by the launcher
+};
+// Leaves per CTA (log2: 9 or 10) with which the shape can run with every CTA resident, or 0: use the throughput path.
+int fri_small_chunk_log(uint32_t D, uint32_t n_big, size_t n_blobs);
+cudaError_t launch_fri_small(cudaStream_t st, const FriSmallParams &p, int chunk_log);
+
 // Proof of work: best[b] = min nonce in [0, limit) whose raw-compress mix has >= pow_bits trailing
 // zeros (atomicMin; initialise to ~0ull).  The warps of ctas_per_blob CTAs take nonce chunks of each
 // blob in increasing order from next[b] (zeroed here).
