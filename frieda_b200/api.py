@@ -94,7 +94,9 @@ EXPORTS = [
     "frieda_proof_clone", "frieda_proof_serialize", "frieda_proof_deserialize", "frieda_proof_serialize_bincode", "frieda_commit_split_local",
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
-    "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
+    "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks",
+    "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_layer", "frieda_fri_split_combine",
+    "frieda_fri_split_handoff", "frieda_fri_split_finish", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
 
@@ -154,6 +156,12 @@ def load_library(build_if_missing: bool = True):
         "frieda_merkle_combine_peers": (C.c_int, [vp, C.POINTER(C.c_void_p), C.c_uint32, u8p]),
         "frieda_commit_split_peers": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), sz,
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, u8p]),
+        "frieda_fri_split_begin": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
+        "frieda_fri_split_begin_device": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
+        "frieda_fri_split_layer": (C.c_int, [vp, C.c_uint32, vp]),
+        "frieda_fri_split_combine": (C.c_int, [vp, C.c_uint32, vp]),
+        "frieda_fri_split_handoff": (C.c_int, [vp, vp]),
+        "frieda_fri_split_finish": (C.c_int, [vp, vp, vp, vp]),
         "frieda_decode_block": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, vp]),
         "frieda_decode_blocks": (C.c_int, [vp, vp, vp, sz, sz, C.c_uint32, vp, C.POINTER(C.c_uint32)]),
         "frieda_pass_pack": (C.c_int, [vp, vp, sz, sz, sz, vp]),
@@ -499,6 +507,38 @@ class Context:
         out = (C.c_uint8 * 32)()
         self._check(self._L.frieda_merkle_combine(self._h, subroots_dev_ptr, world, out))
         return bytes(out)
+
+    # -- FRI commit phase of one blob split over ranks (frieda_fri_split_*) ------------
+    def fri_split_begin(self, data, seed: Optional[int], cfg: PcsConfig, rank: int, world: int,
+                        device_ptr: Optional[int] = None, length: Optional[int] = None) -> Tuple[int, int, int]:
+        """Returns (n_split_layers, n_layers, handoff_log).  data: host bytes / array, or device_ptr + length."""
+        ns, nl, hl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+        if device_ptr is not None:
+            rc = self._L.frieda_fri_split_begin_device(self._h, device_ptr, length, sp, C.byref(cfg), rank, world,
+                                                       C.byref(ns), C.byref(nl), C.byref(hl))
+        else:
+            a = _as_u8(data)
+            rc = self._L.frieda_fri_split_begin(self._h, a.ctypes.data, a.size, sp, C.byref(cfg), rank, world,
+                                                C.byref(ns), C.byref(nl), C.byref(hl))
+        self._check(rc)
+        return int(ns.value), int(nl.value), int(hl.value)
+
+    def fri_split_layer(self, layer: int, subroot_dev_ptr: int):
+        self._check(self._L.frieda_fri_split_layer(self._h, layer, subroot_dev_ptr))
+
+    def fri_split_combine(self, layer: int, subroots_dev_ptr: int):
+        self._check(self._L.frieda_fri_split_combine(self._h, layer, subroots_dev_ptr))
+
+    def fri_split_handoff(self, cols_local_dev_ptr: int):
+        """This rank's 4 x 2^handoff_log u32 share of the first unsplit layer -> the caller's device buffer."""
+        self._check(self._L.frieda_fri_split_handoff(self._h, cols_local_dev_ptr))
+
+    def fri_split_finish(self, cols_all_dev_ptr: int, n_layers: int, log_last: int):
+        roots = np.zeros((n_layers, 32), dtype=np.uint8)
+        last = np.zeros((1 << log_last, 4), dtype=np.uint32)
+        self._check(self._L.frieda_fri_split_finish(self._h, cols_all_dev_ptr, roots.ctypes.data, last.ctypes.data))
+        return roots, last
 
     # -- erasure recovery ------------------------------------------------------------
     def decode_block(self, block_evals: np.ndarray, length: int, log_blowup_factor: int, block: int) -> bytes:

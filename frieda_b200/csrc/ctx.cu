@@ -68,13 +68,11 @@ struct Plan {
   size_t B = 0;
   uint32_t levels_cfg = 10;  // Merkle per-pass depth chosen for this call
   uint32_t nq = 0;  // n_queries (prove)
-  int small_cl = 0; // != 0: the latency path (fri_small.cu) with 2^small_cl leaves per CTA
   bool keep = false, prove = false, fri = false;
   size_t in_stride = 0;  // bytes between staged blobs
   size_t o_in = 0, o_in2 = 0, o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seeds = 0;
   size_t o_cols[34] = {0}, cols_stride[34] = {0};  // u32 elements per blob
   size_t o_tree[34] = {0}, tree_stride[34] = {0};  // 32-byte slots per blob
-  size_t o_cnt = 0;
   size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0, o_counts = 0, o_lvl = 0, o_offsets = 0, o_totals = 0,
          o_evals = 0;
   size_t total = 0;
@@ -110,7 +108,6 @@ struct frieda_ctx {
   size_t ws_limit = 0;
   uint32_t merkle_levels_big = 3;    // per-pass depth for large batches (env FRIEDA_MERKLE_LEVELS)
   uint32_t merkle_levels_small = 10; // per-pass depth when the grid would not fill the GPU anyway
-  bool small_path = true;            // latency path for a few blobs (env FRIEDA_SMALL_PATH=0 turns it off)
   uint32_t levels_for(size_t n_blobs, uint32_t d) const {
     // CTAs of the bottom pass; below ~4 waves of 148 SMs x 4 CTAs the launch count matters more
     size_t ctas = n_blobs << (d > 10 ? d - 10 : 0);
@@ -160,6 +157,20 @@ struct frieda_ctx {
     if (!profiling || prof_recs.empty()) return;
     cudaEventRecord(prof_recs.back().b, stream);
   }
+  // FRI commit phase of ONE blob split over `world` ranks (frieda_fri_split_*): geometry and workspace offsets
+  struct SplitFri {
+    bool active = false;
+    Geom g;
+    uint32_t rank = 0, world = 1, gl = 0;
+    uint32_t n_split = 0;        // layers 0 .. n_split-1 are committed rank-locally + one exchange of subtree roots
+    uint32_t next_layer = 0;     // next layer expected by frieda_fri_split_layer
+    bool handed_off = false;
+    size_t o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seed = 0, o_top = 0, o_sub = 0;
+    size_t o_cols[34] = {0};     // local columns of layers 0 .. n_split-1 (4 x 2^(D - l - gl) u32)
+    size_t o_tree[34] = {0}, tree_slots[34] = {0};
+    size_t o_full = 0;           // workspace of the unsplit remainder (a Plan laid out behind the split state)
+    uint32_t levels_cfg[34] = {0};
+  } split;
   // introspection
   bool debug_keep = false;
   bool have_last = false;
@@ -309,7 +320,6 @@ void layout(Plan &pl, size_t B, bool stage_input) {
     pl.o_last = bp.take(B * (sizeof(QM31) << g.log_last));
     pl.o_err = bp.take(256);
     pl.o_seeds = bp.take(B * 8);
-    pl.o_cnt = bp.take(B * g.n_layers * 4);
   }
   if (pl.prove) {
     pl.o_best = bp.take(B * 8);
@@ -382,7 +392,10 @@ int run_tree(frieda_ctx *ctx, int src, MerkleBottomParams mp, uint32_t d, uint32
     mm.log = u;
     mm.src_level = u;
     mm.chunk_log = 10;
-    mm.levels = levels_cfg < 10 ? levels_cfg : 10;
+    // shallow passes keep every thread hashing, but only pay off while the pass still fills the GPU: with fewer than
+    // ~4 waves of CTAs (one big tree: config 5) a pass is latency-bound and fewer, deeper passes are faster
+    const size_t ctas = n_blobs << (u - 10);
+    mm.levels = (levels_cfg < 10 && ctas >= 2368) ? levels_cfg : 10;
     if (mm.levels > u - 10) mm.levels = u - 10;  // stop exactly where the top kernel takes over
     KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, n_blobs), 1);
     u -= mm.levels;
@@ -420,19 +433,6 @@ int commit_tree(frieda_ctx *ctx, const Plan &pl, uint32_t layer, int src, Channe
   mp.tree_stride = pl.tree_stride[layer];
   QM31 *alpha = chan ? at<QM31>(ctx, pl.o_alpha) + layer : nullptr;
   return run_tree(ctx, src, mp, d, pl.levels_cfg, pl.keep, pl.B, roots, roots_stride, chan, alpha, g.n_layers);
-}
-
-// Few blobs: the FRI layers above the tail as one cooperative launch (fri_small.cu) when every CTA of it can be
-// resident.  The kept / truncated tree layout follows its chunk size.  FRIEDA_SMALL_PATH=0 disables it (A/B probes).
-void choose_small_path(frieda_ctx *ctx, Plan &pl, size_t n) {
-  pl.small_cl = 0;
-  if (!ctx->small_path || n > 8) return;
-  uint32_t n_big = 0;
-  while (n_big < pl.g.n_layers && layer_log(pl.g, n_big) > TAIL_LOG) n_big++;
-  const int cl = fri_small_chunk_log(pl.g.D, n_big, n);
-  if (!cl) return;
-  pl.small_cl = cl;
-  pl.levels_cfg = (uint32_t)cl;
 }
 
 CPoint half_initial_point(const Geom &g) { return host::point_from_index(half_odds_index(g.D - 1, 0)); }
@@ -537,60 +537,11 @@ int fri_wave(frieda_ctx *ctx, const Plan &w, const uint8_t *d_in, size_t d_strid
   uint8_t *roots = at<uint8_t>(ctx, w.o_roots);
   const size_t roots_stride = (size_t)g.n_layers * 32;
   uint32_t layer = 0;
-  if (w.small_cl) {
-    // latency path: channel initialisation and every layer above the tail in one cooperative launch
-    FriSmallParams sp;
-    std::memset(&sp, 0, sizeof sp);
-    while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
-      sp.cols[layer] = at<uint32_t>(ctx, w.o_cols[layer]);
-      sp.cols_stride[layer] = w.cols_stride[layer];
-      sp.tree[layer] = at<uint8_t>(ctx, w.o_tree[layer]);
-      sp.tree_stride[layer] = w.tree_stride[layer];
-      layer++;
-    }
-    sp.n_big = layer;
-    sp.D = g.D;
-    sp.n_blobs = (uint32_t)w.B;
-    sp.write_all = w.keep ? 1 : 0;
-    sp.seeds = d_seeds;
-    sp.roots = roots;
-    sp.roots_stride = roots_stride;
-    sp.chan = chan;
-    sp.alpha = at<QM31>(ctx, w.o_alpha);
-    sp.alpha_stride = g.n_layers;
-    sp.counters = at<uint32_t>(ctx, w.o_cnt);
-    static unsigned long long *dbg = nullptr;
-    if (std::getenv("FRIEDA_SMALL_TRACE") && !dbg) cudaMalloc(&dbg, 8 * (256 + 3 * 1024));
-    sp.trace = std::getenv("FRIEDA_SMALL_TRACE") ? dbg : nullptr;
-    sp.tt = table(ctx);
-    KL("fri_small", launch_fri_small(ctx->stream, sp, w.small_cl), 1);
-    if (sp.trace) {  // FRIEDA_SMALL_TRACE=1: per-layer stage times of CTA 0 on stderr (development aid)
-      {
-        static unsigned long long tt2[3 * 1024];
-        cudaMemcpyAsync(tt2, sp.trace + 256, sizeof tt2, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        unsigned long long t0 = ~0ull;
-        for (int i = 0; i < 256; i++) t0 = tt2[3 * i + 1] < t0 ? tt2[3 * i + 1] : t0;
-        for (int i = 0; i < 256; i += 8)
-          std::fprintf(stderr, "[cta %3d] sm %3llu start %6.2f end %6.2f\n", i, tt2[3 * i], (tt2[3 * i + 1] - t0) / 1e3,
-                       (tt2[3 * i + 2] - t0) / 1e3);
-      }
-      unsigned long long t[6 * 32];
-      CU(cudaMemcpyAsync(t, sp.trace, sizeof(unsigned long long) * 6 * sp.n_big, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      for (uint32_t l = 0; l < sp.n_big; l++)
-        std::fprintf(stderr, "[fri_small] layer %2u log %2u: leaves %6.2f  chunk %6.2f  wait %6.2f  top %6.2f  channel %6.2f us\n",
-                     l, layer_log(g, l), (t[6 * l + 1] - t[6 * l]) / 1e3, (t[6 * l + 2] - t[6 * l + 1]) / 1e3,
-                     (t[6 * l + 3] - t[6 * l + 2]) / 1e3, (t[6 * l + 4] - t[6 * l + 3]) / 1e3,
-                     (t[6 * l + 5] - t[6 * l + 4]) / 1e3);
-    }
-  } else {
-    KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
-    while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
-      int src = layer == 0 ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
-      if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
-      layer++;
-    }
+  KL("channel_init", launch_channel_init(ctx->stream, chan, d_seeds, w.B), 1);
+  while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
+    int src = layer == 0 ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
+    if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
+    layer++;
   }
   const uint32_t s = layer;  // first layer handled by the tail (== n_layers: only the last evaluation)
   const uint32_t s_log = s < g.n_layers ? layer_log(g, s) : g.last_log;
@@ -643,10 +594,8 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
   pl.fri = true;
   pl.keep = ctx->debug_keep;
   pl.levels_cfg = ctx->levels_for(n, pl.g.D);
-  choose_small_path(ctx, pl, n);
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, !device_io, 0);
-  if (B < n) pl.small_cl = 0;  // (a few blobs that do not fit one wave: the throughput path handles waves)
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   const Geom &g = pl.g;
   const cudaMemcpyKind out_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -813,11 +762,9 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   pl.prove = true;
   pl.keep = true;
   pl.levels_cfg = ctx->levels_for(n, pl.g.D);
-  choose_small_path(ctx, pl, n);
   const uint32_t nq = (uint32_t)cfg->n_queries;
   if ((rc = ensure_twiddles(ctx, pl.g.D - 1))) return rc;
   size_t B = pick_wave(ctx, pl, n, true, nq);
-  if (B < n) pl.small_cl = 0;
   tr.mark("plan");
   if ((rc = ensure_arena(ctx, pl.total))) return rc;
   tr.mark("arena");
@@ -996,7 +943,6 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
     delete ctx;
     return FRIEDA_ERR_CUDA;
   }
-  if (const char *ev = std::getenv("FRIEDA_SMALL_PATH")) ctx->small_path = ev[0] != '0';
   if (const char *ev = std::getenv("FRIEDA_MERKLE_LEVELS")) {
     int v = std::atoi(ev);
     if (v >= 1 && v <= 10) ctx->merkle_levels_big = (uint32_t)v;
@@ -1344,6 +1290,290 @@ int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t w
   KL("merkle_top", launch_merkle_top(ctx->stream, tree, 2 * (size_t)world, gl, 0, nullptr, 0, nullptr, nullptr, 0, 1), 1);
   CU(cudaMemcpyAsync(root_out, tree + 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return FRIEDA_OK;
+}
+
+
+// ---- FRI commit phase of one oversized blob split over GPUs (src/proof.rs:38-57 on a blob that
+//      exceeds one GPU) ------------------------------------------------------------------------------------------
+// Rank r of world = 2^g owns the bit-reversed index range [r N_l / world, (r+1) N_l / world) of EVERY layer: fold pairs
+// (2i, 2i+1) are rank-local, so a layer costs one exchange of `world` 32-byte subtree roots (the caller's all-gather:
+// NCCL over NVLink, or peer memory) and every rank then hashes the top g levels and runs the channel step itself.
+// Once a rank's share of a layer is down to 2^SPLIT_MIN_LOG points the layer is gathered and finished on every rank
+// by the ordinary single-GPU path.  Call order on every rank:
+//   begin -> for l in 0 .. n_split-1: { layer(l) -> [all-gather subtree roots] -> combine(l) } -> handoff
+//         -> [all-gather local columns] -> finish
+namespace {
+constexpr uint32_t SPLIT_MIN_LOG = 10;  // smallest rank-local layer that is still committed split
+
+int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool device_input, const uint64_t *seed_or_null,
+                     const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_out,
+                     uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  ctx->split.active = false;
+  if ((!data && len) || !cfg) return ctx->fail_arg("null pointer");
+  if (world == 0 || (world & (world - 1)) || world > MAX_PEERS || rank >= world)
+    return ctx->fail_arg("world must be a power of two <= 64 and > rank");
+  CU(cudaSetDevice(ctx->device));
+  frieda_ctx::SplitFri sp;
+  int rc = make_geom_fri(ctx, len, cfg, sp.g);
+  if (rc) return rc;
+  const Geom &g = sp.g;
+  sp.rank = rank;
+  sp.world = world;
+  while ((1u << sp.gl) < world) sp.gl++;
+  // committed layers whose rank-local share still has 2^SPLIT_MIN_LOG points
+  sp.n_split = 0;
+  while (sp.n_split < g.n_layers && g.D - sp.n_split >= sp.gl + SPLIT_MIN_LOG) sp.n_split++;
+  if (sp.n_split == 0) return ctx->fail_arg("blob too small to split over this many ranks: use frieda_fri_commit_batch");
+  const uint32_t rlog = g.D - sp.gl;
+  if (g.p > 15 && rlog < 14) return ctx->fail_arg("owned range too small for this polynomial size");
+  if ((rc = ensure_twiddles(ctx, g.D - 1))) return rc;
+  Bump bp;
+  size_t o_in = bp.take(align_up(len ? len : 1, 16));
+  sp.o_coef = bp.take((size_t)16 << g.p);
+  for (uint32_t l = 0; l < sp.n_split; l++) sp.o_cols[l] = bp.take((size_t)16 << (layer_log(g, l) - sp.gl));
+  for (uint32_t l = 0; l < sp.n_split; l++) {
+    const uint32_t d = layer_log(g, l) - sp.gl;
+    sp.levels_cfg[l] = ctx->levels_for(1, d);
+    sp.tree_slots[l] = tree_slots(d, false, sp.levels_cfg[l]);
+    sp.o_tree[l] = bp.take(sp.tree_slots[l] * 32);
+  }
+  sp.o_chan = bp.take(sizeof(Channel));
+  sp.o_alpha = bp.take(g.n_layers * sizeof(QM31));
+  sp.o_roots = bp.take((size_t)g.n_layers * 32);
+  sp.o_last = bp.take(sizeof(QM31) << g.log_last);
+  sp.o_err = bp.take(256);
+  sp.o_seed = bp.take(256);
+  sp.o_top = bp.take(2 * (size_t)MAX_PEERS * 32);
+  sp.o_sub = bp.take(32);
+  sp.o_full = bp.off;
+  // remainder: full columns of layers n_split .. n_layers (+ last evaluation) and their trees, all small
+  {
+    Bump fb;
+    fb.off = sp.o_full;
+    for (uint32_t l = sp.n_split; l <= g.n_layers; l++) fb.take((size_t)16 << (l < g.n_layers ? layer_log(g, l) : g.last_log));
+    for (uint32_t l = sp.n_split; l < g.n_layers; l++) fb.take(tree_slots(layer_log(g, l), false, 10) * 32);
+    fb.take(4096);
+    bp.off = fb.off;
+  }
+  if ((rc = ensure_arena(ctx, bp.off))) return rc;
+  ctx->have_last = false;
+  const uint8_t *d_in = data;
+  if (!device_input) {
+    uint8_t *stage = at<uint8_t>(ctx, o_in);
+    if (len) CU(cudaMemcpyAsync(stage, data, len, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = stage;
+  }
+  uint32_t *coef = at<uint32_t>(ctx, sp.o_coef);
+  KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
+  LdeRange rg{(size_t)rank << rlog, rlog};
+  KL("lde", launch_lde(ctx->stream, coef, at<uint32_t>(ctx, sp.o_cols[0]), g.p, g.beta, 1, g.n_felts, table(ctx),
+                       half_initial_point(g), &rg),
+     (g.p > 15 ? 2 : 1));
+  const uint64_t *d_seed = nullptr;
+  if (seed_or_null) {
+    CU(cudaMemcpyAsync(at<uint64_t>(ctx, sp.o_seed), seed_or_null, 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_seed = at<uint64_t>(ctx, sp.o_seed);
+  }
+  KL("channel_init", launch_channel_init(ctx->stream, at<Channel>(ctx, sp.o_chan), d_seed, 1), 1);
+  CU(cudaMemsetAsync(at<int>(ctx, sp.o_err), 0, sizeof(int), ctx->stream));
+  sp.next_layer = 0;
+  sp.handed_off = false;
+  sp.active = true;
+  ctx->split = sp;
+  if (n_split_out) *n_split_out = sp.n_split;
+  if (n_layers_out) *n_layers_out = g.n_layers;
+  if (handoff_log_out) *handoff_log_out = layer_log(g, sp.n_split - 1) - sp.gl - 1;
+  return FRIEDA_OK;
+}
+}  // namespace
+
+int frieda_fri_split_begin(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_layers_out,
+                           uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+  return split_begin_impl(ctx, data, len, false, seed_or_null, cfg, rank, world, n_split_layers_out, n_layers_out,
+                          handoff_log_out);
+}
+int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, const uint64_t *seed_or_null,
+                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world,
+                                  uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+  return split_begin_impl(ctx, d_data, len, true, seed_or_null, cfg, rank, world, n_split_layers_out, n_layers_out,
+                          handoff_log_out);
+}
+
+// Layer `layer` of this rank's range: fold of the previous layer with its alpha (layers >= 1) fused into the leaf
+// hashing, rank-local subtree -> 32-byte subtree root (device memory, the all-gather's input).  Asynchronous.
+int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress (call frieda_fri_split_begin)");
+  if (!d_subroot_out) return ctx->fail_arg("null pointer");
+  if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
+  CU(cudaSetDevice(ctx->device));
+  const Geom &g = sp.g;
+  const uint32_t d = layer_log(g, layer) - sp.gl;  // log size of this rank's share
+  MerkleBottomParams mp;
+  std::memset(&mp, 0, sizeof mp);
+  TwiddleTable tt = table(ctx);
+  int src = SRC_COLS;
+  if (layer == 0) {
+    mp.src_cols = at<uint32_t>(ctx, sp.o_cols[0]);
+    mp.src_stride = (size_t)4 << d;
+  } else {
+    src = layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE;
+    mp.src_cols = at<uint32_t>(ctx, sp.o_cols[layer - 1]);
+    mp.src_stride = (size_t)4 << (d + 1);
+    mp.dst_cols = at<uint32_t>(ctx, sp.o_cols[layer]);
+    mp.dst_stride = (size_t)4 << d;
+    mp.alpha = at<QM31>(ctx, sp.o_alpha) + (layer - 1);
+    mp.alpha_stride = g.n_layers;
+    // twiddle of pair i of the WHOLE layer: this rank's pairs start at rank * 2^d
+    const size_t pair0 = (size_t)sp.rank << d;
+    mp.itw_blk = src == SRC_FOLD_CIRCLE ? tt.iblk(1u << (g.D - 2)) + 2 * (pair0 >> 2)
+                                        : tt.iblk(1u << layer_log(g, layer)) + pair0;
+  }
+  mp.tree = at<uint8_t>(ctx, sp.o_tree[layer]);
+  mp.tree_stride = sp.tree_slots[layer];
+  int rc = run_tree(ctx, src, mp, d, sp.levels_cfg[layer], false, 1, nullptr, 0, nullptr, nullptr, 0);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  return FRIEDA_OK;
+}
+
+// Top log2(world) levels over the gathered subtree roots (d_subroots = world * 32 bytes, rank order, device), then the
+// Fiat-Shamir step of the layer (mix_root, draw alpha) on this rank's copy of the channel.  Asynchronous.
+int frieda_fri_split_combine(frieda_ctx *ctx, uint32_t layer, const uint8_t *d_subroots) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress");
+  if (!d_subroots) return ctx->fail_arg("null pointer");
+  if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
+  CU(cudaSetDevice(ctx->device));
+  const Geom &g = sp.g;
+  uint8_t *top = at<uint8_t>(ctx, sp.o_top);  // heap order: the subtree roots are level gl
+  CU(cudaMemcpyAsync(top + (size_t)sp.world * 32, d_subroots, (size_t)sp.world * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  KL("merkle_top", launch_merkle_top(ctx->stream, top, 2 * (size_t)sp.world, sp.gl, 0, at<uint8_t>(ctx, sp.o_roots) + 32 * (size_t)layer,
+                                     (size_t)g.n_layers * 32, at<Channel>(ctx, sp.o_chan), at<QM31>(ctx, sp.o_alpha) + layer,
+                                     g.n_layers, 1),
+     1);
+  sp.next_layer = layer + 1;
+  return FRIEDA_OK;
+}
+
+// After the last split layer: folds it into this rank's share of the first unsplit layer, written to the caller's
+// buffer d_cols_local_out (4 columns x 2^handoff_log u32, device; the all-gather's input).  Asynchronous.
+int frieda_fri_split_handoff(frieda_ctx *ctx, uint32_t *d_cols_local_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress");
+  if (!d_cols_local_out) return ctx->fail_arg("null pointer");
+  if (sp.next_layer != sp.n_split) return ctx->fail_arg("split layers are not all committed yet");
+  CU(cudaSetDevice(ctx->device));
+  const Geom &g = sp.g;
+  const uint32_t s = sp.n_split;
+  const uint32_t src_log = layer_log(g, s - 1), local_src = src_log - sp.gl;
+  KL("fold", launch_fold_range(ctx->stream, at<uint32_t>(ctx, sp.o_cols[s - 1]), src_log, local_src, (size_t)sp.rank << local_src,
+                               s - 1 == 0, at<QM31>(ctx, sp.o_alpha) + (s - 1), table(ctx), d_cols_local_out),
+     1);
+  sp.handed_off = true;
+  return FRIEDA_OK;
+}
+
+// d_cols_all = world x (4 columns x 2^local_log u32), rank order (the all-gather of the handoff pieces).  Finishes
+// FriProver::commit on this rank from the first unsplit layer with the ordinary single-GPU kernels; every rank
+// computes the same bytes.  layer_roots_out = n_layers * 32 bytes, last_poly_out = 2^log_last QM31 (host).
+int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t *layer_roots_out,
+                            frieda_qm31 *last_poly_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || !sp.handed_off) return ctx->fail_arg("frieda_fri_split_handoff has not been called");
+  if (!d_cols_all || !layer_roots_out || !last_poly_out) return ctx->fail_arg("null pointer");
+  CU(cudaSetDevice(ctx->device));
+  const Geom &g = sp.g;
+  const uint32_t s = sp.n_split;
+  // a one-blob wave whose layers >= s live behind the split state; roots / alpha / channel are the split state's
+  Plan w;
+  w.g = g;
+  w.B = 1;
+  w.fri = true;
+  w.keep = false;
+  w.levels_cfg = 10;
+  {
+    Bump fb;
+    fb.off = sp.o_full;
+    for (uint32_t l = s; l <= g.n_layers; l++) {
+      const uint32_t lg = l < g.n_layers ? layer_log(g, l) : g.last_log;
+      w.cols_stride[l] = (size_t)4 << lg;
+      w.o_cols[l] = fb.take((size_t)16 << lg);
+    }
+    for (uint32_t l = s; l < g.n_layers; l++) {
+      w.tree_stride[l] = tree_slots(layer_log(g, l), false, 10);
+      w.o_tree[l] = fb.take(w.tree_stride[l] * 32);
+    }
+  }
+  w.o_chan = sp.o_chan;
+  w.o_alpha = sp.o_alpha;
+  w.o_roots = sp.o_roots;
+  w.o_last = sp.o_last;
+  w.o_err = sp.o_err;
+  // [rank][column][2^m] -> [column][rank * 2^m ..]
+  const uint32_t full_log = s < g.n_layers ? layer_log(g, s) : g.last_log, m = full_log - sp.gl;
+  for (uint32_t c = 0; c < 4; c++)
+    CU(cudaMemcpy2DAsync(at<uint32_t>(ctx, w.o_cols[s]) + ((size_t)c << full_log), sizeof(uint32_t) << m,
+                         d_cols_all + ((size_t)c << m), sizeof(uint32_t) * 4 << m, sizeof(uint32_t) << m, sp.world,
+                         cudaMemcpyDeviceToDevice, ctx->stream));
+  int rc;
+  Channel *chan = at<Channel>(ctx, w.o_chan);
+  uint8_t *roots = at<uint8_t>(ctx, w.o_roots);
+  const size_t roots_stride = (size_t)g.n_layers * 32;
+  uint32_t layer = s;
+  while (layer < g.n_layers && layer_log(g, layer) > TAIL_LOG) {
+    // the first layer here has its columns already (gathered); the following ones are folded as usual
+    int src = layer == s ? SRC_COLS : (layer == 1 ? SRC_FOLD_CIRCLE : SRC_FOLD_LINE);
+    if ((rc = commit_tree(ctx, w, layer, src, chan, roots + 32 * (size_t)layer, roots_stride))) return rc;
+    layer++;
+  }
+  const uint32_t t0 = layer;  // first layer handled by the tail
+  if (t0 > s) {
+    const uint32_t src_log = layer_log(g, t0 - 1);
+    KL("fold", launch_fold(ctx->stream, at<uint32_t>(ctx, w.o_cols[t0 - 1]), w.cols_stride[t0 - 1], src_log, t0 - 1 == 0,
+                           at<QM31>(ctx, w.o_alpha) + (t0 - 1), g.n_layers, table(ctx), at<uint32_t>(ctx, w.o_cols[t0]),
+                           w.cols_stride[t0], 1),
+       1);
+  }
+  TailParams tp;
+  std::memset(&tp, 0, sizeof tp);
+  for (uint32_t l = s; l <= g.n_layers; l++) {
+    tp.cols[l] = at<uint32_t>(ctx, w.o_cols[l]);
+    tp.cols_stride[l] = w.cols_stride[l];
+    if (l < g.n_layers) {
+      tp.tree[l] = at<uint8_t>(ctx, w.o_tree[l]);
+      tp.tree_stride[l] = w.tree_stride[l];
+    }
+  }
+  tp.write_all = 0;
+  tp.start_layer = t0;
+  tp.start_log = t0 < g.n_layers ? layer_log(g, t0) : g.last_log;
+  tp.last_log = g.last_log;
+  tp.log_last = g.log_last;
+  tp.inv_last_n = m31_inv(1u << g.last_log);
+  tp.roots = roots;
+  tp.roots_stride = roots_stride;
+  tp.chan = chan;
+  tp.alpha = at<QM31>(ctx, w.o_alpha);
+  tp.alpha_stride = g.n_layers;
+  tp.last_poly = at<QM31>(ctx, w.o_last);
+  tp.error_flag = at<int>(ctx, w.o_err);
+  tp.tt = table(ctx);
+  KL("fri_tail", launch_tail(ctx->stream, tp, 1), 1);
+  int err_flag = 0;
+  CU(cudaMemcpyAsync(layer_roots_out, roots, (size_t)g.n_layers * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(last_poly_out, at<QM31>(ctx, w.o_last), sizeof(QM31) << g.log_last, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, w.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  sp.active = false;
+  if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
   return FRIEDA_OK;
 }
 

@@ -39,6 +39,24 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t *__restrict__ 
   }
 }
 
+// Fold of the slice [lo, lo + 2^local_src_log) of a layer with 2^src_log points (split blob: a rank folds its own
+// index range; pairs (2i, 2i+1) never cross a rank boundary).  lo is a multiple of 2^local_src_log >= 8.
+cudaError_t launch_fold_range(cudaStream_t st, const uint32_t *src_local, uint32_t src_log, uint32_t local_src_log,
+                              size_t lo, int is_circle, const QM31 *alpha, const TwiddleTable &tt, uint32_t *dst_local) {
+  if (local_src_log < 3 || local_src_log > src_log || (lo & (((size_t)1 << local_src_log) - 1))) return cudaErrorInvalidValue;
+  if (is_circle && src_log < 3) return cudaErrorInvalidValue;
+  // pair i of the whole layer uses iblk[i] (line) or the (x, y) pair iblk[2 (i >> 2) ..] (circle): offset by lo / 2 pairs
+  const size_t pair0 = lo >> 1;
+  const uint32_t *iblk = is_circle ? tt.iblk(1u << (src_log - 2)) + 2 * (pair0 >> 2) : tt.iblk(1u << (src_log - 1)) + pair0;
+  const uint32_t dst_log = local_src_log - 1;
+  const size_t n = (size_t)1 << dst_log;
+  unsigned bx = (unsigned)((n + 255) / 256);
+  if (bx > 4096) bx = 4096;
+  fold_kernel<<<dim3(bx, 1), 256, 0, st>>>(src_local, (size_t)4 << local_src_log, dst_log, is_circle, alpha, 1, iblk, dst_local,
+                                           (size_t)4 << dst_log);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fold(cudaStream_t st, const uint32_t *src, size_t src_stride, uint32_t src_log, int is_circle,
                         const QM31 *alpha, size_t alpha_stride, const TwiddleTable &tt, uint32_t *dst,
                         size_t dst_stride, size_t n_blobs) {
@@ -111,7 +129,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
     // leaves
     for (uint32_t j = tid; j < n; j += TAIL_THREADS) {
       uint32_t h[8];
-      merkle_hash_leaf(s_cols[cur][0][j], s_cols[cur][1][j], s_cols[cur][2][j], s_cols[cur][3][j], h, p.one);
+      merkle_hash_leaf(s_cols[cur][0][j], s_cols[cur][1][j], s_cols[cur][2][j], s_cols[cur][3][j], h, 1u);  // latency-bound: see merkle_top_kernel
       t_store(&s_ha[j], h);
       if (p.write_all || log == 0) t_store(tree + n + j, h);
     }
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) fri_tail_kernel(const __grid_con
       for (uint32_t j = tid; j < cnt; j += TAIL_THREADS) {
         uint32_t m[16], h[8];
         t_load_pair(hc + 2 * j, m);
-        merkle_hash_node(m, h, p.one);
+        merkle_hash_node(m, h, 1u);
         t_store(&hn[j], h);
         if (p.write_all || level == 1) t_store(tree + cnt + j, h);
       }

@@ -103,6 +103,9 @@ cudaError_t launch_fold(cudaStream_t st, const uint32_t *src, size_t src_stride,
                         const QM31 *alpha, size_t alpha_stride, const TwiddleTable &tt, uint32_t *dst,
                         size_t dst_stride, size_t n_blobs);
 
+cudaError_t launch_fold_range(cudaStream_t st, const uint32_t *src_local, uint32_t src_log, uint32_t local_src_log,
+                              size_t lo, int is_circle, const QM31 *alpha, const TwiddleTable &tt, uint32_t *dst_local);
+
 struct TailParams {
   // layer `start_layer` (log = start_log) is resident in cols[start_layer]; the tail commits it,
   // folds on, and finishes the FRI commit phase inside one CTA per blob.
@@ -128,30 +131,6 @@ struct TailParams {
 constexpr uint32_t TAIL_LOG = 9;      // layers with log <= TAIL_LOG are finished by the tail kernel
 constexpr uint32_t TAIL_LAST_MAX = 9; // largest supported log_last + log_blowup
 cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs);
-
-// Latency path (fri_small.cu): layers 0 .. n_big-1 (those with more than 2^TAIL_LOG points) of a few blobs in ONE
-// cooperative launch, channel initialisation included; fold + fri_tail_kernel finish as usual.
-struct FriSmallParams {
-  uint32_t *cols[32];   // per layer: columns base (layer 0 read, layers >= 1 written)
-  size_t cols_stride[32];
-  uint8_t *tree[32];
-  size_t tree_stride[32];
-  uint32_t n_big, D, n_blobs;
-  int write_all;
-  const uint64_t *seeds;  // device, or nullptr
-  uint8_t *roots;         // [blob][n_layers][32]
-  size_t roots_stride;
-  Channel *chan;
-  QM31 *alpha;            // [blob][layer]
-  size_t alpha_stride;
-  uint32_t *counters;     // [n_big][n_blobs], zeroed by the launcher
-  unsigned long long *trace;  // development aid: 6 globaltimer stamps per layer from CTA 0 (or nullptr)
-  TwiddleTable tt;
-  uint32_t one;           // runtime 1 (blake2s.cuh); set by the launcher
-};
-// Leaves per CTA (log2: 9 or 10) with which the shape can run with every CTA resident, or 0: use the throughput path.
-int fri_small_chunk_log(uint32_t D, uint32_t n_big, size_t n_blobs);
-cudaError_t launch_fri_small(cudaStream_t st, const FriSmallParams &p, int chunk_log);
 
 // Proof of work: best[b] = min nonce in [0, limit) whose raw-compress mix has >= pow_bits trailing
 // zeros (atomicMin; initialise to ~0ull).  The warps of ctas_per_blob CTAs take nonce chunks of each

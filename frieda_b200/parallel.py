@@ -119,6 +119,52 @@ def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: in
                                   st.h_flags.buffer_ptrs, st.epoch)
 
 
+def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,
+                     all_gather=None):
+    """FriProver::commit (src/proof.rs:52-57) of ONE blob with every layer split across the ranks of `group`
+    (frieda_fri_split_*): per split layer a rank-local fused fold + subtree, an all-gather of `world` 32-byte
+    subtree roots (NCCL over NVLink), the top levels and the channel step on every rank; then an all-gather of the
+    first unsplit layer's columns and the ordinary kernels.  Every rank passes the same data / seed / cfg and returns
+    the same (layer_roots (n_layers, 32) uint8, last_layer_poly (2^log_last, 4) uint32), bit-identical to
+    Context.fri_commit_batch on one GPU.
+
+    all_gather(tensor) -> tensor of shape (world, *tensor.shape): the transport; default torch.distributed over
+    `group` (tests with several contexts on one GPU pass their own)."""
+    import torch
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    if world is None:
+        world = dist.get_world_size(group) if distributed else 1
+    if rank is None:
+        rank = dist.get_rank(group) if distributed else 0
+    if not is_pow2(world):
+        raise ValueError("fri_commit_split needs a power-of-two number of ranks")
+    import contextlib
+    on_gpu = getattr(ctx, "is_cuda", True)  # (the CPU tests of this sequencing drive a stand-in context over gloo)
+    dev = torch.device("cuda", ctx.device) if on_gpu else torch.device("cpu")
+    # the collectives are ordered on the context's stream, like its kernels
+    scope = torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)) if on_gpu else contextlib.nullcontext()
+    if all_gather is None:
+        def all_gather(t):
+            if world == 1:
+                return t.reshape((1,) + tuple(t.shape))
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
+            return out
+    n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world)
+    sub = torch.zeros(32, dtype=torch.uint8, device=dev)
+    with scope:
+        for layer in range(n_split):
+            ctx.fri_split_layer(layer, sub.data_ptr())
+            roots = all_gather(sub)
+            ctx.fri_split_combine(layer, roots.data_ptr())
+        mine = torch.empty(4 << handoff_log, dtype=torch.int32, device=dev)
+        ctx.fri_split_handoff(mine.data_ptr())
+        cols_all = all_gather(mine)
+        out = ctx.fri_split_finish(cols_all.data_ptr(), n_layers, cfg.log_last_layer_degree_bound)
+    return out
+
+
 def commit_split(ctx, data, log_blowup_factor: int, group=None, rank: Optional[int] = None,
                  world: Optional[int] = None, sharded_upload: Optional[bool] = None,
                  peer_memory: Optional[bool] = None) -> bytes:

@@ -217,6 +217,36 @@ int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t w
 int frieda_merkle_combine_peers(frieda_ctx *ctx, const uint8_t *const *peer_roots, uint32_t world,
                                 uint8_t root_out[32]);
 
+/* ---- FRI commit phase of ONE oversized blob split across GPUs (FriProver::commit of src/proof.rs:52-57
+ *      for a blob that exceeds one GPU).  Rank r of world = 2^g owns the bit-reversed index range
+ *      [r N_l / world, (r+1) N_l / world) of every layer: fold pairs are rank-local, a layer costs one all-gather of
+ *      `world` 32-byte subtree roots, and every rank hashes the top g levels and runs mix_root / draw_felt itself.
+ *      When a rank's share of a layer is down to 2^10 points the layer is all-gathered and the rest runs on every
+ *      rank with the single-GPU kernels.  The exchanges are the CALLER's (NCCL all-gather over NVLink, or any other
+ *      transport); every call but `finish` is asynchronous on frieda_ctx_stream().  Call order on every rank:
+ *        begin; for l in 0 .. n_split-1: { layer(l); all-gather roots; combine(l) }; handoff; all-gather columns; finish
+ *      No other call may use the context in between (the state lives in its workspace).  Results are bit-identical
+ *      to frieda_fri_commit_batch on one GPU. ------------------------------------------------------------------- */
+int frieda_fri_split_begin(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_layers_out,
+                           uint32_t *n_layers_out, uint32_t *handoff_log_out);
+/* Same with the whole blob already in device memory. */
+int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, const uint64_t *seed_or_null,
+                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world,
+                                  uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out);
+/* Layer `layer` on this rank's range (fold of the previous layer fused into the leaf hashing) -> its subtree root,
+ * 32 bytes of device memory (the all-gather's input). */
+int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out);
+/* d_subroots: world * 32 bytes, rank order, device.  Top levels, root of the layer, mix_root, draw alpha. */
+int frieda_fri_split_combine(frieda_ctx *ctx, uint32_t layer, const uint8_t *d_subroots);
+/* Folds the last split layer into this rank's share of the next one, written to d_cols_local_out: 4 columns x
+ * 2^handoff_log u32 of the caller's device memory (handoff_log from `begin`) -- the input of the all-gather of columns. */
+int frieda_fri_split_handoff(frieda_ctx *ctx, uint32_t *d_cols_local_out);
+/* d_cols_all: world x (4 x 2^handoff_log u32), rank order, device.  layer_roots_out: n_layers * 32 bytes,
+ * last_poly_out: 2^log_last_layer_degree_bound QM31 (host).  Synchronises; FRIEDA_ERR_PANIC on "invalid degree". */
+int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t *layer_roots_out,
+                            frieda_qm31 *last_poly_out);
+
 /* ---- erasure recovery (the reference's README.md:56-70 promises sampling/recovery, its code has none) --
  * The committed evaluation is a Reed-Solomon codeword of rate 2^-log_blowup made of 2^log_blowup coset blocks; ANY ONE
  * whole block determines the data.  block_evals (host): 4 columns x 2^poly_log u32 = entries

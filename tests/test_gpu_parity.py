@@ -717,6 +717,68 @@ def test_commit_config5_64MiB_split_and_unsplit(ctx, torch_mod, golden):
             assert ctx.merkle_combine(subs.data_ptr(), world).hex() == g["root"], (g["name"], world)
 
 
+# ------------------------------------------------------------------ split-blob FRI commit phase
+@pytest.mark.parametrize("kind,n_bytes,seed,cfg,worlds", [
+    ("splitmix", 1 << 20, 11, (2, 0, 20, 12), (1, 2, 4, 8)),   # poly_log 17: strided LDE on a partial range
+    ("splitmix", 8 << 20, None, (2, 0, 20, 12), (2, 8)),       # poly_log 20
+    ("splitmix", 131072, 3, (4, 0, 20, 20), (2, 4, 16)),       # C2 shape
+    ("blob", 262146, None, (4, 1, 20, 20), (4,)),              # the reference's blob and config (src/proof.rs:109-116)
+    ("splitmix", 131072, 9, (4, 5, 20, 20), (1, 2)),           # world 1: every committed layer is split, the tail
+                                                               # starts from the gathered last evaluation
+    ("pattern", 40000, 5, (3, 1, 17, 10), (2, 8)),
+])
+def test_fri_commit_split_virtual_ranks(torch_mod, blob_bytes, kind, n_bytes, seed, cfg, worlds):
+    # G contexts on ONE GPU play the ranks in lockstep; the exchanges are plain device copies.  Layer roots and the
+    # last-layer polynomial of EVERY rank must equal the oracle's FriProver::commit of the whole blob.
+    torch = torch_mod
+    data = blob_bytes if kind == "blob" else case_data(kind, n_bytes)
+    oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
+    pcs = F.PcsConfig(*cfg)
+    for world in worlds:
+        ctxs = [F.Context(0) for _ in range(world)]
+        try:
+            shapes = [c.fri_split_begin(data, seed, pcs, r, world) for r, c in enumerate(ctxs)]
+            assert len(set(shapes)) == 1
+            n_split, n_layers, handoff_log = shapes[0]
+            assert n_layers == len(oroots) and 1 <= n_split <= n_layers
+            for layer in range(n_split):
+                subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+                for r, c in enumerate(ctxs):
+                    c.fri_split_layer(layer, subs[r].data_ptr())
+                torch.cuda.synchronize()
+                for c in ctxs:
+                    c.fri_split_combine(layer, subs.data_ptr())
+                torch.cuda.synchronize()
+            cols = torch.zeros((world, 4 << handoff_log), dtype=torch.int32, device="cuda")
+            for r, c in enumerate(ctxs):
+                c.fri_split_handoff(cols[r].data_ptr())
+            torch.cuda.synchronize()
+            for r, c in enumerate(ctxs):
+                roots, last = c.fri_split_finish(cols.data_ptr(), n_layers, cfg[1])
+                assert [x.tobytes() for x in roots] == oroots, (world, r)
+                assert [tuple(int(x) for x in q) for q in last] == olast, (world, r)
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+def test_fri_commit_split_driver_single_rank_and_errors(ctx):
+    from frieda_b200.parallel import fri_commit_split
+    data = O.splitmix64_bytes(0x4652494544414236, 300000)
+    cfg = (3, 0, 20, 8)
+    roots, last = fri_commit_split(ctx, data, 21, F.PcsConfig(*cfg))
+    oroots, olast = O.fri_commit(data, 21, O.make_config(*cfg))
+    assert [x.tobytes() for x in roots] == oroots and [tuple(int(x) for x in q) for q in last] == olast
+    with pytest.raises(F.FriedaError):          # out of order
+        ctx.fri_split_begin(data, None, F.PcsConfig(*cfg), 0, 1)
+        ctx.fri_split_combine(0, 0)
+    with pytest.raises(F.FriedaError):          # too small to split over 64 ranks
+        ctx.fri_split_begin(pattern(2000), None, F.PcsConfig(2, 0, 8, 2), 0, 64)
+    with pytest.raises(F.FriedaError):
+        ctx.fri_split_layer(0, 1)               # no split in progress after the failed begin
+    assert ctx.commit(b"abc", 3) == O.commit(b"abc", 3)
+
+
 # ------------------------------------------------------------------ GPU batch verification
 def test_verify_batch_matches_host_verifier(ctx):
     cfg = (4, 0, 20, 12)

@@ -28,6 +28,13 @@ for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3)):
             want = O.commit(data.tobytes(), blow)
             assert parallel.commit_split(ctx, data, blow, peer_memory=peers) == want, (n_bytes, blow, peers, k)
 assert not parallel._peer_memory_broken
+# FRI commit phase of one blob with every layer split over the two ranks (NCCL all-gathers of the subtree roots)
+for n_bytes, cfg, seed in ((1 << 20, (2, 0, 20, 12), 7), (131072, (4, 0, 20, 20), None), (8 << 20, (2, 1, 20, 12), 3)):
+    data = O.splitmix64_bytes(0x4652494544414236 + n_bytes, n_bytes)
+    roots, last = parallel.fri_commit_split(ctx, data, seed, F.PcsConfig(*cfg))
+    oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
+    assert [r.tobytes() for r in roots] == oroots, (n_bytes, cfg)
+    assert [tuple(int(x) for x in q) for q in last] == olast, (n_bytes, cfg)
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTI_GPU_OK")

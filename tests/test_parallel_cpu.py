@@ -87,3 +87,90 @@ def test_slice_bounds_cover_the_blob():
                 assert a1 == b0 and a0 <= a1
             assert all(lo % 16 == 0 or lo == n for lo, _ in spans)
             assert all(lo == min(n, r * per) for r, (lo, _) in enumerate(spans)) or n == 0
+
+
+# ------------------------------------------------------------------ split-blob FRI: the driver's sequencing over gloo
+class _OracleSplitCtx:
+    """Stand-in for a CUDA context behind parallel.fri_commit_split: every frieda_fri_split_* step answered from the
+    oracle's trace of the whole blob, restricted to this rank's index range -- and every INPUT the driver hands back
+    (gathered subtree roots, gathered columns) checked against that trace.  Pointers are host addresses here."""
+    is_cuda = False
+    device = 0
+    MIN_LOG = 10  # csrc/ctx.cu: SPLIT_MIN_LOG
+
+    def fri_split_begin(self, data, seed, cfg, rank, world):
+        self.t = O.trace(bytes(data), seed, O.make_config(cfg.log_blowup_factor, cfg.log_last_layer_degree_bound,
+                                                          cfg.n_queries, cfg.pow_bits), stop_after_fri=True, with_trees=True)
+        self.rank, self.world, self.gl = rank, world, world.bit_length() - 1
+        logs = self.t.layer_logs
+        self.n_split = sum(1 for lg in logs if lg >= self.gl + self.MIN_LOG)
+        self.combined = []
+        nxt = logs[self.n_split] if self.n_split < len(logs) else self.t.last_eval.shape[1].bit_length() - 1
+        return self.n_split, len(logs), nxt - self.gl
+
+    def fri_split_layer(self, layer, ptr):
+        import ctypes
+        node = self.t.tree_levels[layer][self.gl][self.rank].tobytes()   # root of my subtree = node (level g, index rank)
+        ctypes.memmove(ptr, node, 32)
+
+    def fri_split_combine(self, layer, ptr):
+        import ctypes
+        got = ctypes.string_at(ptr, 32 * self.world)
+        assert got == self.t.tree_levels[layer][self.gl].tobytes(), f"layer {layer}: gathered subtree roots differ"
+        assert layer == len(self.combined)
+        self.combined.append(layer)
+
+    def _next_cols(self):
+        s = self.n_split
+        return self.t.layer_columns[s] if s < len(self.t.layer_logs) else self.t.last_eval
+
+    def fri_split_handoff(self, ptr):
+        import ctypes
+        assert self.combined == list(range(self.n_split))
+        cols = self._next_cols()
+        m = cols.shape[1] // self.world
+        mine = np.ascontiguousarray(cols[:, self.rank * m:(self.rank + 1) * m])
+        ctypes.memmove(ptr, mine.ctypes.data, mine.nbytes)
+
+    def fri_split_finish(self, ptr, n_layers, log_last):
+        import ctypes
+        cols = self._next_cols()
+        m = cols.shape[1] // self.world
+        got = np.frombuffer(ctypes.string_at(ptr, cols.nbytes), dtype=np.uint32).reshape(self.world, 4, m)
+        want = np.stack([cols[:, r * m:(r + 1) * m] for r in range(self.world)])
+        assert np.array_equal(got, want), "gathered columns are not [rank][column][local index]"
+        roots = np.stack([lv[0].reshape(32) for lv in self.t.tree_levels])
+        return roots, np.array(self.t.last_layer_poly, dtype=np.uint32)
+
+
+def _split_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import frieda_b200 as F
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for n, cfg, seed in ((40000, (3, 1, 8, 4), 5), (131072, (2, 0, 8, 4), None)):
+            data = bytes((i * 7 + n) % 256 for i in range(n))
+            roots, last = parallel.fri_commit_split(_OracleSplitCtx(), data, seed, F.PcsConfig(*cfg))
+            oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
+            ok = ok and [r.tobytes() for r in roots] == oroots and [tuple(int(x) for x in v) for v in last] == olast
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fri_commit_split_sequencing_gloo_world2():
+    import torch.multiprocessing as mp
+    world = 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_split_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
