@@ -432,6 +432,8 @@ def main():
                             "verify_ok": pc["proofs_verify"]}
     if c5 is not None and "ms_per_blob" in c5:
         line["c5"] = {"ms": round(c5["ms_per_blob"], 4), "n": world, "root_ok": c5["root_matches_oracle"],
+                      "ms_resident": (round(c5["ms_per_blob_slices_resident"], 4)
+                                      if c5.get("ms_per_blob_slices_resident") else None),
                       "exchange": c5["exchange_short"], "gb_per_s": round(c5["input_gb_per_s"], 2)}
     if distributed:
         dist.barrier()
@@ -481,7 +483,23 @@ def c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     per = float(dt[0].item()) / iters
     wall_per = float(dt[1].item()) / iters
+    # the same with every rank's slice already in its symmetric buffer (inputs resident in HBM, like `value`)
+    resident_per = None
     from frieda_b200 import parallel as _par
+    if world > 1 and not _par._peer_memory_broken:
+        from frieda_b200.parallel import commit_split_peers
+        host = blob.reshape(-1)
+        assert commit_split_peers(ctx, host, host.size, 2, rank, world, resident=True).hex() == C5_ROOT
+        barrier()
+        ev0.record(stream)
+        for _ in range(iters):
+            ok = ok and commit_split_peers(ctx, host, host.size, 2, rank, world, resident=True).hex() == C5_ROOT
+        ev1.record(stream)
+        stream.synchronize()
+        assert ok, f"rank {rank}/{world}: a split commit from resident slices returned a different root"
+        dr = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dr, op=dist.ReduceOp.MAX)
+        resident_per = float(dr.item()) / iters
     exchange = ("single GPU" if world == 1 else
                 "NCCL all-gathers (peer mapping unavailable)" if _par._peer_memory_broken else
                 "peer-mapped memory: slices and roots read in place over NVLink by the library's kernels")
@@ -489,6 +507,7 @@ def c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier):
             "exchange": exchange,
             "exchange_short": ("single" if world == 1 else "nccl" if _par._peer_memory_broken else "peer"),
             "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "wall_ms_per_blob": wall_per * 1e3,
+            "ms_per_blob_slices_resident": resident_per * 1e3 if resident_per else None,
             "blobs_per_s": 1.0 / per,
             "input_gb_per_s": n_bytes / per / 1e9, "n_gpus": world, "scaling": "strong",
             "timing": "CUDA events on the context's stream around the synchronous calls, max over ranks (H2D of the "

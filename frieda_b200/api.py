@@ -485,12 +485,18 @@ class Context:
                                                             rank, subroot_dev_ptr))
 
     def commit_split_peers(self, data, log_blowup_factor: int, rank: int, peer_slice_ptrs, slice_len: int,
-                           peer_root_ptrs, peer_flag_ptrs, epoch: int) -> bytes:
-        """The whole split commit of this rank in one call (frieda_commit_split_peers): exchanges over peer memory."""
-        a = _as_u8(data)
+                           peer_root_ptrs, peer_flag_ptrs, epoch: int, resident_len: Optional[int] = None) -> bytes:
+        """The whole split commit of this rank in one call (frieda_commit_split_peers): exchanges over peer memory.
+        resident_len: the blob's length when every rank's slice already lies in its symmetric buffer (data ignored)."""
         world = len(peer_slice_ptrs)
         mk = lambda ps: (C.c_void_p * world)(*[int(p) for p in ps])  # noqa: E731
         out = (C.c_uint8 * 32)()
+        if resident_len is not None:
+            self._check(self._L.frieda_commit_split_peers(self._h, None, resident_len, log_blowup_factor, rank, world,
+                                                          mk(peer_slice_ptrs), slice_len, mk(peer_root_ptrs),
+                                                          mk(peer_flag_ptrs), epoch, out))
+            return bytes(out)
+        a = _as_u8(data)
         self._check(self._L.frieda_commit_split_peers(self._h, a.ctypes.data, a.size, log_blowup_factor, rank, world,
                                                       mk(peer_slice_ptrs), slice_len, mk(peer_root_ptrs),
                                                       mk(peer_flag_ptrs), epoch, out))

@@ -1121,7 +1121,9 @@ int frieda_prove_batch(frieda_ctx *ctx, const uint8_t *blobs, size_t blob_len, s
 // call returns without synchronising the stream.
 static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup,
                                    uint32_t rank, uint32_t world, uint8_t *d_subroot_out, bool device_input,
-                                   const PeerPtrs *peers = nullptr, size_t slice_len = 0, bool prepare_only = false) {
+                                   const PeerPtrs *peers = nullptr, size_t slice_len = 0, bool prepare_only = false,
+                                   const uint32_t *wait_flags = nullptr, uint32_t part_len = 0, uint32_t epoch = 0,
+                                   int *timeout_flag = nullptr) {
   if (!ctx) return FRIEDA_ERR_ARG;
   if ((!data && !peers && len) || !d_subroot_out) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || rank >= world) return ctx->fail_arg("world must be a power of two > rank");
@@ -1157,7 +1159,9 @@ static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t 
   uint32_t *coef = at<uint32_t>(ctx, o_coef);
   uint32_t *eval = at<uint32_t>(ctx, o_eval);
   if (peers)
-    KL("pack_peers", launch_pack_peers(ctx->stream, *peers, world, rank, slice_len, len, g.n_felts, g.p, coef), 1);
+    KL("pack_peers", launch_pack_peers(ctx->stream, *peers, world, rank, slice_len, len, g.n_felts, g.p, coef, wait_flags,
+                                       part_len, epoch, timeout_flag),
+       1);
   else
     KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
   LdeRange rg{(size_t)rank << rlog, rlog};
@@ -1169,8 +1173,11 @@ static int commit_split_local_impl(frieda_ctx *ctx, const uint8_t *data, size_t 
   mp.src_stride = (size_t)4 << rlog;
   mp.tree = at<uint8_t>(ctx, o_tree);
   mp.tree_stride = slots;
-  if ((rc = run_tree(ctx, SRC_COLS, mp, rlog, lv, false, 1, nullptr, 0, nullptr, nullptr, 0))) return rc;
-  CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  // the top kernel stores the subtree root straight into the caller's slot when that is 16-byte aligned
+  const bool direct = (reinterpret_cast<uintptr_t>(d_subroot_out) & 15) == 0;
+  if ((rc = run_tree(ctx, SRC_COLS, mp, rlog, lv, false, 1, direct ? d_subroot_out : nullptr, 32, nullptr, nullptr, 0)))
+    return rc;
+  if (!direct) CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
   if (!peers) CU(cudaStreamSynchronize(ctx->stream));
   return FRIEDA_OK;
 }
@@ -1204,7 +1211,8 @@ int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, 
                               uint8_t *const *peer_roots, uint32_t *const *peer_flags, uint32_t epoch,
                               uint8_t root_out[32]) {
   if (!ctx) return FRIEDA_ERR_ARG;
-  if ((!data && len) || !peer_slices || !peer_roots || !peer_flags || !root_out) return ctx->fail_arg("null pointer");
+  // data == nullptr: this rank's slice already lies in peer_slices[rank] (inputs resident in HBM); nothing is uploaded
+  if (!peer_slices || !peer_roots || !peer_flags || !root_out) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || world > MAX_PEERS || rank >= world)
     return ctx->fail_arg("world must be a power of two <= 64 and > rank");
   if (slice_len == 0 || (slice_len & 15) || (uint64_t)slice_len * world < len)
@@ -1227,15 +1235,41 @@ int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, 
   CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
   // my slice of the input, over my own PCIe link
   const size_t lo = std::min(len, (size_t)rank * slice_len), hi = std::min(len, lo + slice_len);
-  if (hi > lo) CU(cudaMemcpyAsync(peer_slices[rank], data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-  KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 0, epoch, d_timeout), 1);
-  rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len);
+  Geom g;
+  if ((rc = make_geom(ctx, len, log_blowup, g))) return rc;
+  const bool pipelined = ((size_t)4 << g.p) >= 4096 && slice_len >= ((size_t)1 << 20) && slice_len < ((size_t)1 << 31);
+  if (pipelined) {
+    // Upload in PEER_UPLOAD_PARTS parts on the copy stream, each followed by a signal to every rank; the packing
+    // kernel on the compute stream waits per part, so it (and the NVLink reads of the early parts) overlap the rest
+    // of the upload instead of starting behind a full barrier.  A slice is not overwritten while a peer may still read
+    // the previous call's bytes: every rank's packing precedes its arrival at barrier 1 of that call.
+    const uint32_t part_len = (uint32_t)align_up((slice_len + PEER_UPLOAD_PARTS - 1) / PEER_UPLOAD_PARTS, 16);
+    CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+    for (uint32_t k = 0; k < PEER_UPLOAD_PARTS; k++) {
+      const size_t a = std::min(hi, lo + (size_t)k * part_len), b = std::min(hi, a + part_len);
+      if (b > a && data)
+        CU(cudaMemcpyAsync(peer_slices[rank] + (a - lo), data + a, b - a, cudaMemcpyHostToDevice, ctx->copy_stream));
+      cudaError_t e = launch_peer_signal(ctx->copy_stream, fl, world, rank, 2 + k, epoch);
+      if (e != cudaSuccess) return ctx->fail(e, "launch_peer_signal", __LINE__);
+      ctx->launches += 1;
+    }
+    CU(cudaEventRecord(ctx->ev_copied[0], ctx->copy_stream));
+    rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len, false,
+                                 peer_flags[rank], part_len, epoch, d_timeout);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[0], 0));
+  } else {
+    if (hi > lo && data) CU(cudaMemcpyAsync(peer_slices[rank], data + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+    KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, world, rank, 0, epoch, d_timeout), 1);
+    rc = commit_split_local_impl(ctx, nullptr, len, log_blowup, rank, world, peer_roots[rank], true, &sl, slice_len);
+  }
   if (rc) {
-    // a launch failed after the first barrier: still arrive at the second one so the peers fail fast on the
-    // root they read (this rank reports its own error) instead of spinning until the barrier's timeout
+    // a launch failed after the peers may already depend on this rank: still arrive at the second barrier so they fail
+    // fast on the root they read (this rank reports its own error) instead of spinning until the barrier's timeout
     const std::string keep = ctx->err;
     launch_peer_barrier(ctx->stream, fl, world, rank, 1, epoch, d_timeout);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaGetLastError();
     ctx->err = keep;
     return rc;

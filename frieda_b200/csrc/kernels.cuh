@@ -63,8 +63,12 @@ constexpr uint32_t MAX_PEERS = 64;
 struct PeerPtrs {
   const uint8_t *p[MAX_PEERS];
 };
+// wait_flags != nullptr (this rank's flag array): the slices are uploaded in parts of part_len bytes while this kernel
+// runs; part k of slice s may be read once flag (2 + k, s) >= epoch (launch_peer_signal by its owner).
 cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t world, uint32_t rank, size_t slice_len,
-                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef);
+                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef,
+                              const uint32_t *wait_flags = nullptr, uint32_t part_len = 0, uint32_t epoch = 0,
+                              int *timeout_flag = nullptr);
 // tree slot (world + r) <- 32 bytes at roots.p[r]  (the leaves of the top tree of a split commit)
 cudaError_t launch_gather_roots(cudaStream_t st, const PeerPtrs &roots, uint32_t world, uint8_t *tree);
 // Barrier between the GPUs of a split commit, on the stream: every rank stores `epoch` into word
@@ -74,6 +78,11 @@ cudaError_t launch_gather_roots(cudaStream_t st, const PeerPtrs &roots, uint32_t
 struct PeerFlags {
   uint32_t *p[MAX_PEERS];
 };
+// flag (channel, rank) of an array = word channel * MAX_PEERS + rank: channels 0 / 1 = the two barriers, 2 .. 5 = "part
+// k of rank's slice is uploaded"; an array holds PEER_FLAG_CHANNELS * MAX_PEERS = 512 words
+constexpr uint32_t PEER_FLAG_CHANNELS = 8, PEER_UPLOAD_PARTS = 4;
+cudaError_t launch_peer_signal(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
+                               uint32_t epoch);
 cudaError_t launch_peer_barrier(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
                                 uint32_t epoch, int *timeout_flag);
 cudaError_t launch_twiddles(cudaStream_t st, const GenPowers &gp, uint32_t K, uint32_t *tw, uint32_t *itw,

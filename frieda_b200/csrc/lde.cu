@@ -52,8 +52,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ b
 }
 
 constexpr uint32_t PP_LIMBS = 4096, PP_BYTES = 15360;  // 4 x (1024 limbs = 3840 bytes) per CTA iteration
+struct PackWait {  // pipelined upload (frieda_commit_split_peers): part k of slice s is ready once flag (2 + k, s) >= epoch
+  const uint32_t *my_flags;  // this rank's flag array, or nullptr: no waiting
+  uint32_t part_len, epoch;
+  int *timeout_flag;
+};
 __global__ void pack_peers_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len, uint32_t len, uint32_t n_felts,
-                                  uint32_t n_coef, uint32_t first_chunk, size_t blob_stride, uint32_t *__restrict__ coef_all);
+                                  uint32_t n_coef, uint32_t first_chunk, size_t blob_stride, uint32_t *__restrict__ coef_all,
+                                  PackWait pw);
 
 cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_t stride, size_t n_blobs,
                         uint32_t n_felts, uint32_t poly_log, uint32_t *coef) {
@@ -68,7 +74,7 @@ cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_
       size_t nb = n_blobs - b0 < 65535 ? n_blobs - b0 : 65535;
       one.p[0] = blobs + b0 * stride;
       pack_peers_kernel<<<dim3(n_coef / PP_LIMBS, (unsigned)nb), 256, 0, st>>>(one, slice, (uint32_t)len, n_felts, n_coef, 0,
-                                                                              stride, coef + b0 * n_coef);
+                                                                              stride, coef + b0 * n_coef, PackWait{});
     }
     return cudaGetLastError();
   }
@@ -90,7 +96,7 @@ cudaError_t launch_pack(cudaStream_t st, const uint8_t *blobs, size_t len, size_
 __global__ void __launch_bounds__(256) pack_peers_kernel(const __grid_constant__ PeerPtrs sl, uint32_t slice_len,
                                                           uint32_t len, uint32_t n_felts, uint32_t n_coef,
                                                           uint32_t first_chunk, size_t blob_stride,
-                                                          uint32_t *__restrict__ coef_all) {
+                                                          uint32_t *__restrict__ coef_all, PackWait pw) {
   __shared__ __align__(16) uint32_t w[PP_BYTES / 4 + 4];
   const uint32_t t = threadIdx.x, n_chunks = n_coef / PP_LIMBS;
   const size_t in_off = (size_t)blockIdx.y * blob_stride;
@@ -104,6 +110,28 @@ __global__ void __launch_bounds__(256) pack_peers_kernel(const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 4; i++) reinterpret_cast<uint4 *>(coef + k0)[t + 256 * i] = make_uint4(0u, 0u, 0u, 0u);
       continue;
+    }
+    if (pw.my_flags) {
+      // The slices are still being uploaded, part by part: wait for the (at most two) parts this chunk's bytes lie in.
+      // A part's owner raises flag (2 + part, owner) in every rank's array after its copy (system-scope release).
+      if (t < 2) {
+        uint32_t byte = c * PP_BYTES + (t ? PP_BYTES - 1 : 0);
+        if (byte >= len) byte = len - 1;
+        const uint32_t s = byte / slice_len, part = (byte - s * slice_len) / pw.part_len;
+        const uint32_t *flag = pw.my_flags + (2 + part) * MAX_PEERS + s;
+        const long long t0 = clock64();
+        for (;;) {
+          uint32_t v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if ((int32_t)(v - pw.epoch) >= 0) break;
+          if (clock64() - t0 > 40000000000ll) {  // ~20 s: the owner of that slice is gone
+            atomicExch(pw.timeout_flag, 1);
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
+      __syncthreads();
     }
     uint4 v[4];
 #pragma unroll
@@ -165,8 +193,25 @@ __global__ void pack_peers_small_kernel(const __grid_constant__ PeerPtrs sl, uin
   coef[k] = val;
 }
 
+// Raises flag (channel, rank) = epoch in every rank's flag array (system-scope release): "everything this rank put
+// on the stream before this kernel -- the upload of one part of its slice -- is done".
+__global__ void peer_signal_kernel(const __grid_constant__ PeerFlags flags, uint32_t world, uint32_t rank, uint32_t channel,
+                                   uint32_t epoch) {
+  const uint32_t j = threadIdx.x;
+  if (j >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[j] + channel * MAX_PEERS + rank), "r"(epoch) : "memory");
+}
+cudaError_t launch_peer_signal(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
+                               uint32_t epoch) {
+  if (world == 0 || world > MAX_PEERS || rank >= world || channel >= PEER_FLAG_CHANNELS) return cudaErrorInvalidValue;
+  peer_signal_kernel<<<1, MAX_PEERS, 0, st>>>(flags, world, rank, channel, epoch);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t world, uint32_t rank, size_t slice_len,
-                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef) {
+                              size_t len, uint32_t n_felts, uint32_t poly_log, uint32_t *coef, const uint32_t *wait_flags,
+                              uint32_t part_len, uint32_t epoch, int *timeout_flag) {
   if (world == 0 || world > MAX_PEERS || slice_len == 0 || (slice_len & 15) || len >= ((size_t)1 << 31) ||
       slice_len >= ((size_t)1 << 31))
     return cudaErrorInvalidValue;
@@ -174,15 +219,26 @@ cudaError_t launch_pack_peers(cudaStream_t st, const PeerPtrs &slices, uint32_t 
     if ((reinterpret_cast<uintptr_t>(slices.p[r]) & 15) != 0) return cudaErrorInvalidValue;
   const uint32_t n_coef = 4u << poly_log;
   if (n_coef < PP_LIMBS) {
+    if (wait_flags) return cudaErrorInvalidValue;  // (callers use a full barrier for inputs this small)
     pack_peers_small_kernel<<<(n_coef + 127) / 128, 128, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts,
                                                                  n_coef, coef);
     return cudaGetLastError();
   }
   uint32_t bx = n_coef / PP_LIMBS;
   if (bx > 148 * 64) bx = 148 * 64;
+  if (wait_flags) {
+    // CTAs of this kernel spin until the part they need is uploaded, and the kernels that announce the parts (on the
+    // copy stream, this GPU's own among them) need an SM to run on: never let the waiting grid fill the machine
+    // (2 CTAs of 256 threads x 64 registers per SM leave half of every SM's threads, registers and shared memory free;
+    // with 4 the register file was full and the signal kernels starved -- every rank then waited out the time limit)
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (bx > (uint32_t)sms * 2) bx = (uint32_t)sms * 2;
+  }
   // chunk holding the first byte of this rank's slice
   const uint32_t first_chunk = (uint32_t)(((uint64_t)rank * slice_len / PP_BYTES) % (n_coef / PP_LIMBS));
-  pack_peers_kernel<<<bx, 256, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts, n_coef, first_chunk, 0, coef);
+  pack_peers_kernel<<<bx, 256, 0, st>>>(slices, (uint32_t)slice_len, (uint32_t)len, n_felts, n_coef, first_chunk, 0, coef,
+                                        PackWait{wait_flags, part_len, epoch, timeout_flag});
   return cudaGetLastError();
 }
 
@@ -221,7 +277,7 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags flags, uin
 }
 cudaError_t launch_peer_barrier(cudaStream_t st, const PeerFlags &flags, uint32_t world, uint32_t rank, uint32_t channel,
                                 uint32_t epoch, int *timeout_flag) {
-  if (world == 0 || world > MAX_PEERS || rank >= world || channel > 1) return cudaErrorInvalidValue;
+  if (world == 0 || world > MAX_PEERS || rank >= world || channel >= PEER_FLAG_CHANNELS) return cudaErrorInvalidValue;
   peer_barrier_kernel<<<1, MAX_PEERS, 0, st>>>(flags, world, rank, channel, epoch, timeout_flag);
   return cudaGetLastError();
 }

@@ -64,13 +64,18 @@ class _PeerState:
         self.h_in = symm_mem.rendezvous(self.buf, group=g)
         self.roots = symm_mem.empty(64 * 32, dtype=torch.uint8, device=dev)
         self.h_roots = symm_mem.rendezvous(self.roots, group=g)
-        # signal words of the library's own stream-ordered barriers (2 channels x 64 ranks), zero before first use
-        self.flags = symm_mem.empty(128, dtype=torch.int32, device=dev)
+        # signal words of the library's own stream-ordered barriers and upload flags (8 channels x 64 ranks), zero
+        # before first use
+        self.flags = symm_mem.empty(512, dtype=torch.int32, device=dev)
         self.flags.zero_()
         self.h_flags = symm_mem.rendezvous(self.flags, group=g)
         self.h_flags.barrier(channel=0)
         torch.cuda.current_stream(dev).synchronize()
         self.epoch = 0
+        # the pointer lists handed to the library on every call (the properties rebuild them on each access)
+        self.slice_ptrs = [int(p) for p in self.h_in.buffer_ptrs]
+        self.root_ptrs = [int(p) + 32 * r for r, p in enumerate(self.h_roots.buffer_ptrs)]
+        self.flag_ptrs = [int(p) for p in self.h_flags.buffer_ptrs]
 
 
 _peer_states = {}
@@ -104,7 +109,7 @@ def _peer_state(ctx, group, slice_len: int):
 
 
 def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: int, world: int, group=None,
-                       st=None) -> bytes:
+                       st=None, resident: bool = False) -> bytes:
     """The split commit over peer memory: ONE library call, ordered on the context's stream with one host
     synchronisation at the end (frieda_commit_split_peers): upload my slice -> barrier kernel -> pack straight
     out of the peers' slices (the all-gather is the packing kernel's loads over NVLink) -> LDE + Merkle of my
@@ -114,9 +119,9 @@ def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: in
     if st is None:
         st = _peer_state(ctx, group, per)
     st.epoch += 1
-    return ctx.commit_split_peers(host, log_blowup_factor, rank, st.h_in.buffer_ptrs, per,
-                                  [int(p) + 32 * r for r, p in enumerate(st.h_roots.buffer_ptrs)],
-                                  st.h_flags.buffer_ptrs, st.epoch)
+    # resident: the slices of a previous call with the same blob are still in the symmetric buffers (inputs in HBM)
+    return ctx.commit_split_peers(host, log_blowup_factor, rank, st.slice_ptrs, per, st.root_ptrs, st.flag_ptrs, st.epoch,
+                                  resident_len=n_bytes if resident else None)
 
 
 def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,

@@ -202,7 +202,10 @@ int frieda_commit_split_local_peers(frieda_ctx *ctx, const uint8_t *const *peer_
  * peer-mapped memory (no NCCL on the data path): upload this rank's slice (host bytes
  * [rank * slice_len, ...)) into peer_slices[rank] -> barrier -> pack from all slices in place -> LDE + Merkle
  * subtree -> root into peer_roots[rank] -> barrier -> combine reading peer_roots[*] in place -> root_out (host).
- * peer_flags[r]: 128 u32 of zero-initialised peer-mapped memory per rank (the barriers' signal words);
+ * peer_flags[r]: 512 u32 of zero-initialised peer-mapped memory per rank (signal words: two barriers and the
+ * per-part "uploaded" flags -- slices of 1 MiB and more are uploaded in four parts on a second stream while the packing
+ * kernel already reads the parts that have arrived);
+ * data == NULL: this rank's slice already lies in peer_slices[rank] (inputs resident in HBM); nothing is uploaded.
  * epoch: a counter that every rank increases by one per call, starting at 1.  One host synchronisation.
  * Returns FRIEDA_ERR_CUDA with "peer barrier timed out" if a peer does not arrive within ~20 s. */
 int frieda_commit_split_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, uint32_t log_blowup, uint32_t rank,

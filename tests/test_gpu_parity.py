@@ -678,12 +678,24 @@ def test_commit_split_peers_single_rank(ctx, torch_mod):
     per = (len(data) + 15) // 16 * 16
     sl = torch.empty(per, dtype=torch.uint8, device="cuda")
     roots = torch.zeros(64 * 32, dtype=torch.uint8, device="cuda")
-    flags = torch.zeros(128, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(512, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     for epoch in (1, 2, 3):
         got = ctx.commit_split_peers(data, 3, 0, [sl.data_ptr()], per, [roots.data_ptr()], [flags.data_ptr()], epoch)
         assert got == O.commit(data, 3)
     assert flags.cpu().tolist()[0] == 3 and flags.cpu().tolist()[64] == 3
+    # a slice of 1 MiB and more is uploaded in four parts on the copy stream, the packing kernel waiting per part
+    big = O.splitmix64_bytes(0x4652494544414236, (3 << 20) + 77)
+    per = (len(big) + 15) // 16 * 16
+    sl = torch.empty(per, dtype=torch.uint8, device="cuda")
+    for epoch in (4, 5):
+        assert ctx.commit_split_peers(big, 2, 0, [sl.data_ptr()], per, [roots.data_ptr()], [flags.data_ptr()],
+                                      epoch) == O.commit(big, 2)
+    # data = NULL: the slice is already in the buffer (inputs resident in HBM), nothing is uploaded
+    assert ctx.commit_split_peers(None, 2, 0, [sl.data_ptr()], per, [roots.data_ptr()], [flags.data_ptr()], 6,
+                                  resident_len=len(big)) == O.commit(big, 2)
+    f = flags.cpu().tolist()
+    assert f[0] == 3 and f[64] == 6 and [f[64 * c] for c in (2, 3, 4, 5)] == [6, 6, 6, 6]
 
 
 def test_commit_split_single_process_api(ctx):

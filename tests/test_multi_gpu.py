@@ -19,7 +19,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = F.Context(local)
-for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3)):
+# (8 MiB: slices of 4 MiB are uploaded in parts while the packing kernel of BOTH ranks already waits for them)
+for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3), (8 << 20, 2)):
     for peers in (False, True):
         # repeated calls reuse the symmetric buffers and advance the barrier epoch; the CONTENT changes every call, so
         # a peer reading a stale copy of another rank's slice or root would give a wrong root
