@@ -157,8 +157,9 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
             return out
     n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world)
-    sub = torch.zeros(32, dtype=torch.uint8, device=dev)
     with scope:
+        # (allocated inside the scope: every tensor the library writes is touched on the context's stream only)
+        sub = torch.empty(32, dtype=torch.uint8, device=dev)
         for layer in range(n_split):
             ctx.fri_split_layer(layer, sub.data_ptr())
             roots = all_gather(sub)

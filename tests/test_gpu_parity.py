@@ -637,6 +637,7 @@ def test_commit_split_virtual_ranks(ctx, torch_mod, n_bytes, blow, worlds):
     assert ctx.commit(data, blow) == want
     for world in worlds:
         subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         for r in range(world):
             ctx.commit_split_local(data, blow, r, world, subs[r].data_ptr())
         assert ctx.merkle_combine(subs.data_ptr(), world) == want, world
@@ -710,6 +711,7 @@ def test_commit_split_subroots_are_tree_nodes(ctx, torch_mod):
     t = O.trace(data, None, O.make_config(2, 0, 4, 1), stop_after_fri=True, with_trees=True)
     world = 4
     subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     for r in range(world):
         ctx.commit_split_local(data, 2, r, world, subs[r].data_ptr())
     assert subs.cpu().numpy().tobytes() == t.tree_levels[0][2].tobytes()
@@ -724,6 +726,7 @@ def test_commit_config5_64MiB_split_and_unsplit(ctx, torch_mod, golden):
         assert ctx.commit(data, g["log_blowup"]).hex() == g["root"], g["name"]
         for world in (2, 8):
             subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
             for r in range(world):
                 ctx.commit_split_local(data, g["log_blowup"], r, world, subs[r].data_ptr())
             assert ctx.merkle_combine(subs.data_ptr(), world).hex() == g["root"], (g["name"], world)
@@ -755,6 +758,7 @@ def test_fri_commit_split_virtual_ranks(torch_mod, blob_bytes, kind, n_bytes, se
             assert n_layers == len(oroots) and 1 <= n_split <= n_layers
             for layer in range(n_split):
                 subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()  # the fill runs on torch's stream, the library on its own non-blocking ones
                 for r, c in enumerate(ctxs):
                     c.fri_split_layer(layer, subs[r].data_ptr())
                 torch.cuda.synchronize()
@@ -762,6 +766,7 @@ def test_fri_commit_split_virtual_ranks(torch_mod, blob_bytes, kind, n_bytes, se
                     c.fri_split_combine(layer, subs.data_ptr())
                 torch.cuda.synchronize()
             cols = torch.zeros((world, 4 << handoff_log), dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
             for r, c in enumerate(ctxs):
                 c.fri_split_handoff(cols[r].data_ptr())
             torch.cuda.synchronize()
