@@ -96,7 +96,8 @@ EXPORTS = [
     "frieda_commit_split_peers",
     "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks",
     "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_layer", "frieda_fri_split_combine",
-    "frieda_fri_split_handoff", "frieda_fri_split_finish", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
+    "frieda_fri_split_handoff", "frieda_fri_split_finish", "frieda_fri_split_decommit", "frieda_fri_split_assemble",
+    "frieda_buffer_free", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
 ]
 
@@ -156,8 +157,12 @@ def load_library(build_if_missing: bool = True):
         "frieda_merkle_combine_peers": (C.c_int, [vp, C.POINTER(C.c_void_p), C.c_uint32, u8p]),
         "frieda_commit_split_peers": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), sz,
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, u8p]),
-        "frieda_fri_split_begin": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
-        "frieda_fri_split_begin_device": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, u32p, u32p, u32p]),
+        "frieda_fri_split_begin": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, C.c_int, u32p, u32p, u32p]),
+        "frieda_fri_split_begin_device": (C.c_int, [vp, vp, sz, u64p, cfgp, C.c_uint32, C.c_uint32, C.c_int, u32p, u32p,
+                                                    u32p]),
+        "frieda_fri_split_decommit": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz)]),
+        "frieda_fri_split_assemble": (C.c_int, [C.POINTER(vp), C.POINTER(sz), C.c_uint32, C.POINTER(pp)]),
+        "frieda_buffer_free": (None, [vp]),
         "frieda_fri_split_layer": (C.c_int, [vp, C.c_uint32, vp]),
         "frieda_fri_split_combine": (C.c_int, [vp, C.c_uint32, vp]),
         "frieda_fri_split_handoff": (C.c_int, [vp, vp]),
@@ -516,17 +521,19 @@ class Context:
 
     # -- FRI commit phase of one blob split over ranks (frieda_fri_split_*) ------------
     def fri_split_begin(self, data, seed: Optional[int], cfg: PcsConfig, rank: int, world: int,
-                        device_ptr: Optional[int] = None, length: Optional[int] = None) -> Tuple[int, int, int]:
-        """Returns (n_split_layers, n_layers, handoff_log).  data: host bytes / array, or device_ptr + length."""
+                        device_ptr: Optional[int] = None, length: Optional[int] = None,
+                        keep_trees: bool = False) -> Tuple[int, int, int]:
+        """Returns (n_split_layers, n_layers, handoff_log).  data: host bytes / array, or device_ptr + length.
+        keep_trees: a proof follows (fri_split_decommit)."""
         ns, nl, hl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
         sp = C.byref(C.c_uint64(seed)) if seed is not None else None
         if device_ptr is not None:
             rc = self._L.frieda_fri_split_begin_device(self._h, device_ptr, length, sp, C.byref(cfg), rank, world,
-                                                       C.byref(ns), C.byref(nl), C.byref(hl))
+                                                       int(keep_trees), C.byref(ns), C.byref(nl), C.byref(hl))
         else:
             a = _as_u8(data)
             rc = self._L.frieda_fri_split_begin(self._h, a.ctypes.data, a.size, sp, C.byref(cfg), rank, world,
-                                                C.byref(ns), C.byref(nl), C.byref(hl))
+                                                int(keep_trees), C.byref(ns), C.byref(nl), C.byref(hl))
         self._check(rc)
         return int(ns.value), int(nl.value), int(hl.value)
 
@@ -545,6 +552,16 @@ class Context:
         last = np.zeros((1 << log_last, 4), dtype=np.uint32)
         self._check(self._L.frieda_fri_split_finish(self._h, cols_all_dev_ptr, roots.ctypes.data, last.ctypes.data))
         return roots, last
+
+    def fri_split_decommit(self) -> bytes:
+        """Proof of work, queries and THIS rank's share of the decommitment (after fri_split_finish of a commit begun
+        with keep_trees).  The shares of all ranks, in rank order, go to `split_assemble`."""
+        p, n = C.c_void_p(0), C.c_size_t(0)
+        self._check(self._L.frieda_fri_split_decommit(self._h, C.byref(p), C.byref(n)))
+        try:
+            return C.string_at(p.value, n.value)
+        finally:
+            self._L.frieda_buffer_free(p)
 
     # -- erasure recovery ------------------------------------------------------------
     def decode_block(self, block_evals: np.ndarray, length: int, log_blowup_factor: int, block: int) -> bytes:
@@ -621,6 +638,20 @@ def query_positions(proof: Proof, seed: Optional[int]):
     buf = (C.c_uint32 * max(n, 1))()
     L.frieda_proof_query_positions(proof.ptr, sp, buf, n)
     return [int(buf[i]) for i in range(n)]
+
+
+def split_assemble(shares: Sequence[bytes]) -> Proof:
+    """Merges the per-rank shares of a split blob's decommitment (rank order) into the Proof.  Host only."""
+    L = load_library()
+    world = len(shares)
+    bufs = [np.frombuffer(bytes(s) + b"\0" * (-len(s) % 4), dtype=np.uint8).copy() for s in shares]
+    ptrs = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    lens = (C.c_size_t * world)(*[len(s) for s in shares])
+    p = C.POINTER(ProofStruct)()
+    rc = L.frieda_fri_split_assemble(ptrs, lens, world, C.byref(p))
+    if rc:
+        raise FriedaError(rc, "the shares do not form a proof (different blobs, ranks out of order, or corrupted)")
+    return Proof(p)
 
 
 def verify_core_host(proof: Proof, seed: Optional[int]) -> int:

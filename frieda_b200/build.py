@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfrieda_b200.so")
-SOURCES = ["ctx.cu", "lde.cu", "merkle.cu", "fri.cu", "decommit.cu", "verify_batch.cu", "proof.cpp", "verify.cpp"]
+SOURCES = ["ctx.cu", "lde.cu", "merkle.cu", "fri.cu", "decommit.cu", "verify_batch.cu", "proof.cpp", "verify.cpp", "split_proof.cpp"]
 # host-only sources built by the host compiler with per-file ISA flags (entered only after a runtime CPU check)
 HOST_SOURCES = {"blake2s_x8.cpp": ["-mavx2"], "blake2s_x16.cpp": ["-mavx512f"], "cpu_features.cpp": []}
 NVCC_FLAGS = [

@@ -24,6 +24,7 @@
 #include "ctx_internal.h"
 #include "host_math.hpp"
 #include "kernels.cuh"
+#include "split_plan.hpp"
 
 using namespace frieda;
 
@@ -165,6 +166,12 @@ struct frieda_ctx {
     uint32_t n_split = 0;        // layers 0 .. n_split-1 are committed rank-locally + one exchange of subtree roots
     uint32_t next_layer = 0;     // next layer expected by frieda_fri_split_layer
     bool handed_off = false;
+    bool keep = false;           // trees kept whole: a proof follows (frieda_fri_split_decommit)
+    bool finished = false;       // FriProver::commit is complete, the state is still resident
+    frieda_pcs_config cfg{};
+    size_t o_toptree = 0;        // keep: per split layer the top log2(world) levels (2 * world slots each)
+    size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0;
+    Plan rem;                    // the unsplit remainder as a one-blob wave (valid once finished)
     size_t o_coef = 0, o_chan = 0, o_alpha = 0, o_roots = 0, o_last = 0, o_err = 0, o_seed = 0, o_top = 0, o_sub = 0;
     size_t o_cols[34] = {0};     // local columns of layers 0 .. n_split-1 (4 x 2^(D - l - gl) u32)
     size_t o_tree[34] = {0}, tree_slots[34] = {0};
@@ -1340,8 +1347,36 @@ int frieda_merkle_combine(frieda_ctx *ctx, const uint8_t *d_subroots, uint32_t w
 namespace {
 constexpr uint32_t SPLIT_MIN_LOG = 10;  // smallest rank-local layer that is still committed split
 
+// lays out the unsplit remainder (layers n_split .. n_layers and the last evaluation) behind the split state
+void split_layout_remainder(const frieda_ctx::SplitFri &sp, Plan &w, size_t *end_out) {
+  const Geom &g = sp.g;
+  w = Plan();
+  w.g = g;
+  w.B = 1;
+  w.fri = true;
+  w.keep = sp.keep;
+  w.levels_cfg = 10;
+  Bump fb;
+  fb.off = sp.o_full;
+  for (uint32_t l = sp.n_split; l <= g.n_layers; l++) {
+    const uint32_t lg = l < g.n_layers ? layer_log(g, l) : g.last_log;
+    w.cols_stride[l] = (size_t)4 << lg;
+    w.o_cols[l] = fb.take((size_t)16 << lg);
+  }
+  for (uint32_t l = sp.n_split; l < g.n_layers; l++) {
+    w.tree_stride[l] = tree_slots(layer_log(g, l), sp.keep, 10);
+    w.o_tree[l] = fb.take(w.tree_stride[l] * 32);
+  }
+  w.o_chan = sp.o_chan;
+  w.o_alpha = sp.o_alpha;
+  w.o_roots = sp.o_roots;
+  w.o_last = sp.o_last;
+  w.o_err = sp.o_err;
+  if (end_out) *end_out = fb.off + 4096;
+}
+
 int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool device_input, const uint64_t *seed_or_null,
-                     const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_out,
+                     const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees, uint32_t *n_split_out,
                      uint32_t *n_layers_out, uint32_t *handoff_log_out) {
   if (!ctx) return FRIEDA_ERR_ARG;
   ctx->split.active = false;
@@ -1353,6 +1388,10 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   int rc = make_geom_fri(ctx, len, cfg, sp.g);
   if (rc) return rc;
   const Geom &g = sp.g;
+  sp.keep = keep_trees != 0;
+  sp.cfg = *cfg;
+  if (sp.keep && (cfg->n_queries == 0 || cfg->n_queries > 4096 || cfg->pow_bits > 40))
+    return ctx->fail_arg("n_queries must be in 1..4096 and pow_bits <= 40 for a proof");
   sp.rank = rank;
   sp.world = world;
   while ((1u << sp.gl) < world) sp.gl++;
@@ -1370,8 +1409,15 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   for (uint32_t l = 0; l < sp.n_split; l++) {
     const uint32_t d = layer_log(g, l) - sp.gl;
     sp.levels_cfg[l] = ctx->levels_for(1, d);
-    sp.tree_slots[l] = tree_slots(d, false, sp.levels_cfg[l]);
+    sp.tree_slots[l] = tree_slots(d, sp.keep, sp.levels_cfg[l]);
     sp.o_tree[l] = bp.take(sp.tree_slots[l] * 32);
+  }
+  if (sp.keep) {
+    sp.o_toptree = bp.take((size_t)sp.n_split * 2 * world * 32);
+    sp.o_best = bp.take(8);
+    sp.o_next = bp.take(8);
+    sp.o_nuniq = bp.take(4);
+    sp.o_queries = bp.take((size_t)cfg->n_queries * 4);
   }
   sp.o_chan = bp.take(sizeof(Channel));
   sp.o_alpha = bp.take(g.n_layers * sizeof(QM31));
@@ -1382,14 +1428,11 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   sp.o_top = bp.take(2 * (size_t)MAX_PEERS * 32);
   sp.o_sub = bp.take(32);
   sp.o_full = bp.off;
-  // remainder: full columns of layers n_split .. n_layers (+ last evaluation) and their trees, all small
   {
-    Bump fb;
-    fb.off = sp.o_full;
-    for (uint32_t l = sp.n_split; l <= g.n_layers; l++) fb.take((size_t)16 << (l < g.n_layers ? layer_log(g, l) : g.last_log));
-    for (uint32_t l = sp.n_split; l < g.n_layers; l++) fb.take(tree_slots(layer_log(g, l), false, 10) * 32);
-    fb.take(4096);
-    bp.off = fb.off;
+    Plan tmp;
+    size_t end = 0;
+    split_layout_remainder(sp, tmp, &end);
+    bp.off = end;
   }
   if ((rc = ensure_arena(ctx, bp.off))) return rc;
   ctx->have_last = false;
@@ -1414,6 +1457,7 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   CU(cudaMemsetAsync(at<int>(ctx, sp.o_err), 0, sizeof(int), ctx->stream));
   sp.next_layer = 0;
   sp.handed_off = false;
+  sp.finished = false;
   sp.active = true;
   ctx->split = sp;
   if (n_split_out) *n_split_out = sp.n_split;
@@ -1424,16 +1468,16 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
 }  // namespace
 
 int frieda_fri_split_begin(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
-                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_layers_out,
-                           uint32_t *n_layers_out, uint32_t *handoff_log_out) {
-  return split_begin_impl(ctx, data, len, false, seed_or_null, cfg, rank, world, n_split_layers_out, n_layers_out,
-                          handoff_log_out);
+                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
+                           uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+  return split_begin_impl(ctx, data, len, false, seed_or_null, cfg, rank, world, keep_trees, n_split_layers_out,
+                          n_layers_out, handoff_log_out);
 }
 int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, const uint64_t *seed_or_null,
-                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world,
+                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
                                   uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out) {
-  return split_begin_impl(ctx, d_data, len, true, seed_or_null, cfg, rank, world, n_split_layers_out, n_layers_out,
-                          handoff_log_out);
+  return split_begin_impl(ctx, d_data, len, true, seed_or_null, cfg, rank, world, keep_trees, n_split_layers_out,
+                          n_layers_out, handoff_log_out);
 }
 
 // Layer `layer` of this rank's range: fold of the previous layer with its alpha (layers >= 1) fused into the leaf
@@ -1469,7 +1513,7 @@ int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_o
   }
   mp.tree = at<uint8_t>(ctx, sp.o_tree[layer]);
   mp.tree_stride = sp.tree_slots[layer];
-  int rc = run_tree(ctx, src, mp, d, sp.levels_cfg[layer], false, 1, nullptr, 0, nullptr, nullptr, 0);
+  int rc = run_tree(ctx, src, mp, d, sp.levels_cfg[layer], sp.keep, 1, nullptr, 0, nullptr, nullptr, 0);
   if (rc) return rc;
   CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
   return FRIEDA_OK;
@@ -1485,9 +1529,11 @@ int frieda_fri_split_combine(frieda_ctx *ctx, uint32_t layer, const uint8_t *d_s
   if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
   CU(cudaSetDevice(ctx->device));
   const Geom &g = sp.g;
-  uint8_t *top = at<uint8_t>(ctx, sp.o_top);  // heap order: the subtree roots are level gl
+  // heap order: the subtree roots are level gl; kept per layer when a proof follows (the decommitment's top levels)
+  uint8_t *top = sp.keep ? at<uint8_t>(ctx, sp.o_toptree) + (size_t)layer * 2 * sp.world * 32 : at<uint8_t>(ctx, sp.o_top);
   CU(cudaMemcpyAsync(top + (size_t)sp.world * 32, d_subroots, (size_t)sp.world * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-  KL("merkle_top", launch_merkle_top(ctx->stream, top, 2 * (size_t)sp.world, sp.gl, 0, at<uint8_t>(ctx, sp.o_roots) + 32 * (size_t)layer,
+  KL("merkle_top", launch_merkle_top(ctx->stream, top, 2 * (size_t)sp.world, sp.gl, sp.keep ? 1 : 0,
+                                     at<uint8_t>(ctx, sp.o_roots) + 32 * (size_t)layer,
                                      (size_t)g.n_layers * 32, at<Channel>(ctx, sp.o_chan), at<QM31>(ctx, sp.o_alpha) + layer,
                                      g.n_layers, 1),
      1);
@@ -1527,30 +1573,8 @@ int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t
   const Geom &g = sp.g;
   const uint32_t s = sp.n_split;
   // a one-blob wave whose layers >= s live behind the split state; roots / alpha / channel are the split state's
-  Plan w;
-  w.g = g;
-  w.B = 1;
-  w.fri = true;
-  w.keep = false;
-  w.levels_cfg = 10;
-  {
-    Bump fb;
-    fb.off = sp.o_full;
-    for (uint32_t l = s; l <= g.n_layers; l++) {
-      const uint32_t lg = l < g.n_layers ? layer_log(g, l) : g.last_log;
-      w.cols_stride[l] = (size_t)4 << lg;
-      w.o_cols[l] = fb.take((size_t)16 << lg);
-    }
-    for (uint32_t l = s; l < g.n_layers; l++) {
-      w.tree_stride[l] = tree_slots(layer_log(g, l), false, 10);
-      w.o_tree[l] = fb.take(w.tree_stride[l] * 32);
-    }
-  }
-  w.o_chan = sp.o_chan;
-  w.o_alpha = sp.o_alpha;
-  w.o_roots = sp.o_roots;
-  w.o_last = sp.o_last;
-  w.o_err = sp.o_err;
+  split_layout_remainder(sp, sp.rem, nullptr);
+  const Plan &w = sp.rem;
   // [rank][column][2^m] -> [column][rank * 2^m ..]
   const uint32_t full_log = s < g.n_layers ? layer_log(g, s) : g.last_log, m = full_log - sp.gl;
   for (uint32_t c = 0; c < 4; c++)
@@ -1586,7 +1610,7 @@ int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t
       tp.tree_stride[l] = w.tree_stride[l];
     }
   }
-  tp.write_all = 0;
+  tp.write_all = sp.keep ? 1 : 0;
   tp.start_layer = t0;
   tp.start_log = t0 < g.n_layers ? layer_log(g, t0) : g.last_log;
   tp.last_log = g.last_log;
@@ -1606,8 +1630,123 @@ int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t
   CU(cudaMemcpyAsync(last_poly_out, at<QM31>(ctx, w.o_last), sizeof(QM31) << g.log_last, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, w.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  sp.active = false;
-  if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+  sp.finished = true;
+  if (!sp.keep) sp.active = false;
+  if (err_flag) {
+    sp.active = false;
+    return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+  }
+  return FRIEDA_OK;
+}
+
+// After `finish` of a commit begun with keep_trees: the rest of commit_and_generate_proof (src/proof.rs:58-66) on this
+// rank -- proof of work and queries (replicated: same channel, same nonce, same positions on every rank), then THIS
+// rank's share of the decommitment: the evaluations, sibling values and tree nodes of split_plan.hpp that it holds,
+// gathered by address.  *share_out is malloc'ed (frieda_buffer_free); the shares of all ranks, in rank order, go to
+// frieda_fri_split_assemble on whichever rank wants the Proof.  Ends the split state.
+int frieda_fri_split_decommit(frieda_ctx *ctx, uint8_t **share_out, size_t *share_len_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!share_out || !share_len_out) return ctx->fail_arg("null pointer");
+  *share_out = nullptr;
+  *share_len_out = 0;
+  if (!sp.active || !sp.finished || !sp.keep)
+    return ctx->fail_arg("no finished split FRI commit with kept trees (frieda_fri_split_begin with keep_trees)");
+  CU(cudaSetDevice(ctx->device));
+  sp.active = false;  // whatever happens below, the state is consumed
+  const Geom &g = sp.g;
+  const uint32_t nq = (uint32_t)sp.cfg.n_queries;
+  Channel *chan = at<Channel>(ctx, sp.o_chan);
+  unsigned long long *best = at<unsigned long long>(ctx, sp.o_best);
+  CU(cudaMemsetAsync(best, 0xff, 8, ctx->stream));
+  const uint64_t limit = (uint64_t)1 << (sp.cfg.pow_bits + 12 > 62 ? 62 : sp.cfg.pow_bits + 12);
+  KL("grind", launch_grind(ctx->stream, chan, sp.cfg.pow_bits, limit, 2048, best, at<unsigned long long>(ctx, sp.o_next), 1), 1);
+  uint32_t *d_queries = at<uint32_t>(ctx, sp.o_queries), *d_nuniq = at<uint32_t>(ctx, sp.o_nuniq);
+  KL("queries", launch_queries(ctx->stream, chan, best, g.D, nq, d_queries, d_nuniq, 1), 1);
+  unsigned long long nonce = 0;
+  uint32_t n_unique = 0;
+  std::vector<uint32_t> q(nq);
+  std::vector<uint8_t> roots((size_t)g.n_layers * 32);
+  std::vector<frieda_qm31> last((size_t)1 << g.log_last);
+  CU(cudaMemcpyAsync(&nonce, best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&n_unique, d_nuniq, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(q.data(), d_queries, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(roots.data(), at<uint8_t>(ctx, sp.o_roots), roots.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(last.data(), at<QM31>(ctx, sp.o_last), last.size() * sizeof(frieda_qm31), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (nonce == ~0ull) return ctx->fail_arg("proof of work search exhausted");
+  if (n_unique == 0 || n_unique > nq) return ctx->fail_arg("query sampling failed");
+  // what the proof consists of, and what of it lies on this rank
+  std::vector<SplitItem> items;
+  std::vector<uint32_t> n_fri, n_hash;
+  split_plan(SplitShape{g.D, g.n_layers, sp.n_split, sp.gl}, q.data(), n_unique, items, n_fri, n_hash);
+  std::vector<GatherQ> gq;
+  std::vector<GatherH> gh;
+  for (const SplitItem &it : items) {
+    if (it.owner != sp.rank) continue;
+    const uint32_t d = g.D - it.layer;
+    const bool split = it.layer < sp.n_split;
+    if (it.kind == SK_HASH) {
+      const uint4 *p;
+      if (split && it.level > sp.gl) {  // inside my subtree: local level = level - gl
+        const uint32_t ll = it.level - sp.gl;
+        p = at<uint4>(ctx, sp.o_tree[it.layer]) + 2 * (((size_t)1 << ll) + (it.index - ((size_t)sp.rank << ll)));
+      } else if (split) {               // the replicated top of a split layer's tree
+        p = at<uint4>(ctx, sp.o_toptree) + 2 * ((size_t)it.layer * 2 * sp.world + ((size_t)1 << it.level) + it.index);
+      } else {                          // unsplit layer: the whole tree is here
+        p = at<uint4>(ctx, sp.rem.o_tree[it.layer]) + 2 * (((size_t)1 << it.level) + it.index);
+      }
+      gh.push_back(GatherH{p});
+    } else if (split) {
+      const uint32_t ld = d - sp.gl;
+      gq.push_back(GatherQ{at<uint32_t>(ctx, sp.o_cols[it.layer]) + (it.index - ((size_t)sp.rank << ld)), 1u << ld});
+    } else {
+      gq.push_back(GatherQ{at<uint32_t>(ctx, sp.rem.o_cols[it.layer]) + it.index, 1u << d});
+    }
+  }
+  const size_t dq_bytes = align_up(gq.size() * sizeof(GatherQ) + 16, 256), dh_bytes = align_up(gh.size() * sizeof(GatherH) + 16, 256);
+  const size_t oq_bytes = align_up(gq.size() * 16 + 16, 256), oh_bytes = gh.size() * 32 + 32;
+  int rc = ensure_gather(ctx, dq_bytes + dh_bytes + oq_bytes + oh_bytes);
+  if (rc) return rc;
+  uint8_t *d = ctx->d_gather;
+  if (!gq.empty()) CU(cudaMemcpyAsync(d, gq.data(), gq.size() * sizeof(GatherQ), cudaMemcpyHostToDevice, ctx->stream));
+  if (!gh.empty()) CU(cudaMemcpyAsync(d + dq_bytes, gh.data(), gh.size() * sizeof(GatherH), cudaMemcpyHostToDevice, ctx->stream));
+  KL("gather_items", launch_gather_items(ctx->stream, reinterpret_cast<const GatherQ *>(d), (uint32_t)gq.size(),
+                                         reinterpret_cast<const GatherH *>(d + dq_bytes), (uint32_t)gh.size(),
+                                         reinterpret_cast<QM31 *>(d + dq_bytes + dh_bytes), d + dq_bytes + dh_bytes + oq_bytes),
+     1);
+  // the share: header, transcript results, then my items in proof order
+  const size_t words = sizeof(SplitShareHeader) / 4 + n_unique + (size_t)g.n_layers * 8 + ((size_t)4 << g.log_last) + 2 +
+                       gq.size() * 4 + gh.size() * 8;
+  uint32_t *out = (uint32_t *)std::malloc(words * 4);
+  if (!out) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+  SplitShareHeader h{SPLIT_SHARE_MAGIC, sp.world, sp.rank, sp.gl, g.D, g.n_layers, sp.n_split, g.p,
+                     sp.cfg.log_blowup_factor, sp.cfg.log_last_layer_degree_bound, nq, 0u, sp.cfg.pow_bits,
+                     (uint32_t)nonce, (uint32_t)(nonce >> 32), n_unique};
+  size_t pos = 0;
+  std::memcpy(out, &h, sizeof h);
+  pos += sizeof h / 4;
+  std::memcpy(out + pos, q.data(), (size_t)n_unique * 4);
+  pos += n_unique;
+  std::memcpy(out + pos, roots.data(), roots.size());
+  pos += roots.size() / 4;
+  std::memcpy(out + pos, last.data(), last.size() * sizeof(frieda_qm31));
+  pos += last.size() * 4;
+  out[pos++] = (uint32_t)gq.size();
+  out[pos++] = (uint32_t)gh.size();
+  cudaError_t ce = cudaSuccess;
+  if (!gq.empty())
+    ce = cudaMemcpyAsync(out + pos, d + dq_bytes + dh_bytes, gq.size() * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  pos += gq.size() * 4;
+  if (ce == cudaSuccess && !gh.empty())
+    ce = cudaMemcpyAsync(out + pos, d + dq_bytes + dh_bytes + oq_bytes, gh.size() * 32, cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    std::free(out);
+    return ctx->fail(ce, "split decommit readback", __LINE__);
+  }
+  *share_out = reinterpret_cast<uint8_t *>(out);
+  *share_len_out = words * 4;
   return FRIEDA_OK;
 }
 

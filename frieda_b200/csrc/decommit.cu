@@ -315,6 +315,28 @@ __global__ void evaluations_kernel(const __grid_constant__ DecommitParams p, siz
   p.evals_out[g] = {{cols[pos], cols[n + pos], cols[2 * n + pos], cols[3 * n + pos]}};
 }
 
+// Split blob (frieda_fri_split_decommit): the values and hashes THIS rank holds, picked out by address.
+__global__ void __launch_bounds__(128) gather_items_kernel(const GatherQ *__restrict__ dq, uint32_t n_q,
+                                                           const GatherH *__restrict__ dh, uint32_t n_h,
+                                                           QM31 *__restrict__ out_q, uint4 *__restrict__ out_h) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_q) {
+    const GatherQ d = dq[t];
+    out_q[t] = {{d.p[0], d.p[d.stride], d.p[2 * (size_t)d.stride], d.p[3 * (size_t)d.stride]}};
+  } else if (t < n_q + n_h) {
+    const uint4 *src = dh[t - n_q].p;
+    out_h[2 * (size_t)(t - n_q)] = src[0];
+    out_h[2 * (size_t)(t - n_q) + 1] = src[1];
+  }
+}
+cudaError_t launch_gather_items(cudaStream_t st, const GatherQ *dq, uint32_t n_q, const GatherH *dh, uint32_t n_h,
+                                QM31 *out_q, uint8_t *out_h) {
+  const uint32_t n = n_q + n_h;
+  if (n == 0) return cudaSuccess;
+  gather_items_kernel<<<(n + 127) / 128, 128, 0, st>>>(dq, n_q, dh, n_h, out_q, reinterpret_cast<uint4 *>(out_h));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_decommit_count(cudaStream_t st, const DecommitParams &p, size_t n_blobs) {
   if (p.lvl_stride < p.D) return cudaErrorInvalidValue;
   size_t n = n_blobs * p.n_layers * p.lvl_stride;

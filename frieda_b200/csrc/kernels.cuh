@@ -173,4 +173,15 @@ cudaError_t launch_decommit_count(cudaStream_t st, const DecommitParams &p, size
 cudaError_t launch_decommit_scan(cudaStream_t st, const DecommitParams &p, size_t n_blobs, unsigned long long *totals);
 cudaError_t launch_decommit_write(cudaStream_t st, const DecommitParams &p, size_t n_blobs);
 
+// Gather by address (split-blob decommitment): a QM31 from four columns `stride` words apart, a 32-byte tree node.
+struct GatherQ {
+  const uint32_t *p;
+  uint32_t stride;
+};
+struct GatherH {
+  const uint4 *p;
+};
+cudaError_t launch_gather_items(cudaStream_t st, const GatherQ *dq, uint32_t n_q, const GatherH *dh, uint32_t n_h,
+                                QM31 *out_q, uint8_t *out_h);
+
 }  // namespace frieda

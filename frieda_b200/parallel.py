@@ -124,8 +124,33 @@ def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: in
                                   resident_len=n_bytes if resident else None)
 
 
+def prove_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,
+                all_gather=None, all_gather_bytes=None):
+    """commit_and_generate_proof (src/proof.rs:32-77) of ONE blob split across the ranks of `group`: the split FRI commit
+    with every tree kept, then on every rank proof of work + queries (replicated) and the rank's share of the
+    decommitment; the shares are all-gathered (a few hundred KB) and merged on every rank.  Returns (root, Proof),
+    byte-identical to Context.commit_and_generate_proof on one GPU.
+
+    all_gather_bytes(b) -> list of `world` byte strings in rank order; default torch.distributed.all_gather_object."""
+    import torch.distributed as dist
+    from .api import split_assemble
+    distributed = dist.is_available() and dist.is_initialized()
+    if world is None:
+        world = dist.get_world_size(group) if distributed else 1
+    roots, _ = fri_commit_split(ctx, data, seed, cfg, group, rank, world, all_gather, keep_trees=True)
+    share = ctx.fri_split_decommit()
+    if all_gather_bytes is None:
+        def all_gather_bytes(b):
+            if world == 1:
+                return [b]
+            out = [None] * world
+            dist.all_gather_object(out, b, group=group)
+            return out
+    return roots[0].tobytes(), split_assemble(all_gather_bytes(share))
+
+
 def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,
-                     all_gather=None):
+                     all_gather=None, keep_trees: bool = False):
     """FriProver::commit (src/proof.rs:52-57) of ONE blob with every layer split across the ranks of `group`
     (frieda_fri_split_*): per split layer a rank-local fused fold + subtree, an all-gather of `world` 32-byte
     subtree roots (NCCL over NVLink), the top levels and the channel step on every rank; then an all-gather of the
@@ -156,7 +181,7 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
             return out
-    n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world)
+    n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
     with scope:
         # (allocated inside the scope: every tensor the library writes is touched on the context's stream only)
         sub = torch.empty(32, dtype=torch.uint8, device=dev)

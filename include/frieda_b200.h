@@ -230,12 +230,14 @@ int frieda_merkle_combine_peers(frieda_ctx *ctx, const uint8_t *const *peer_root
  *        begin; for l in 0 .. n_split-1: { layer(l); all-gather roots; combine(l) }; handoff; all-gather columns; finish
  *      No other call may use the context in between (the state lives in its workspace).  Results are bit-identical
  *      to frieda_fri_commit_batch on one GPU. ------------------------------------------------------------------- */
+/* keep_trees != 0: every Merkle tree is kept whole (rank-local subtrees, the replicated top levels, the unsplit
+ * layers) because a proof follows (frieda_fri_split_decommit). */
 int frieda_fri_split_begin(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
-                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, uint32_t *n_split_layers_out,
-                           uint32_t *n_layers_out, uint32_t *handoff_log_out);
+                           const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
+                           uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out);
 /* Same with the whole blob already in device memory. */
 int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, const uint64_t *seed_or_null,
-                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world,
+                                  const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
                                   uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out);
 /* Layer `layer` on this rank's range (fold of the previous layer fused into the leaf hashing) -> its subtree root,
  * 32 bytes of device memory (the all-gather's input). */
@@ -249,6 +251,18 @@ int frieda_fri_split_handoff(frieda_ctx *ctx, uint32_t *d_cols_local_out);
  * last_poly_out: 2^log_last_layer_degree_bound QM31 (host).  Synchronises; FRIEDA_ERR_PANIC on "invalid degree". */
 int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t *layer_roots_out,
                             frieda_qm31 *last_poly_out);
+/* Proof generation for the split blob: the rest of commit_and_generate_proof (src/proof.rs:58-66) after a commit
+ * begun with keep_trees.  Every rank calls frieda_fri_split_decommit after `finish`: proof of work and query
+ * sampling run on every rank (same channel, same nonce, same positions), then the rank gathers ITS share of the
+ * decommitment -- the evaluations, sibling values and tree nodes it holds (owner-serves-path: a rank serves what lies
+ * in its index range / subtree, rank 0 also the replicated top levels and the unsplit layers).  *share_out is a
+ * malloc'ed, relocatable byte string (release with frieda_buffer_free).  frieda_fri_split_assemble (host only, any
+ * rank or any other machine) merges the `world` shares, given in rank order, into the Proof -- byte-identical to the
+ * one frieda_prove returns for the same blob on one GPU.  FRIEDA_ERR_ARG if the shares do not belong together. */
+int frieda_fri_split_decommit(frieda_ctx *ctx, uint8_t **share_out, size_t *share_len_out);
+int frieda_fri_split_assemble(const uint8_t *const *shares, const size_t *share_lens, uint32_t world,
+                              frieda_proof **proof_out);
+void frieda_buffer_free(uint8_t *buffer);
 
 /* ---- erasure recovery (the reference's README.md:56-70 promises sampling/recovery, its code has none) --
  * The committed evaluation is a Reed-Solomon codeword of rate 2^-log_blowup made of 2^log_blowup coset blocks; ANY ONE

@@ -25,7 +25,7 @@ fn main() {
         "--expt-relaxed-constexpr", "-shared", "-x", "cu", "-o",
     ])
     .arg(&lib);
-    for f in ["ctx.cu", "lde.cu", "merkle.cu", "fri.cu", "decommit.cu", "verify_batch.cu", "proof.cpp", "verify.cpp"] {
+    for f in ["ctx.cu", "lde.cu", "merkle.cu", "fri.cu", "decommit.cu", "verify_batch.cu", "proof.cpp", "verify.cpp", "split_proof.cpp"] {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

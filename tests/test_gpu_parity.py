@@ -779,6 +779,78 @@ def test_fri_commit_split_virtual_ranks(torch_mod, blob_bytes, kind, n_bytes, se
                 c.close()
 
 
+def split_prove_virtual(torch, data, seed, cfg, world):
+    """commit_and_generate_proof of one blob over `world` contexts on one GPU (lockstep, device copies as the
+    exchange): returns the per-rank shares of the decommitment."""
+    pcs = F.PcsConfig(*cfg)
+    ctxs = [F.Context(0) for _ in range(world)]
+    try:
+        shapes = [c.fri_split_begin(data, seed, pcs, r, world, keep_trees=True) for r, c in enumerate(ctxs)]
+        n_split, n_layers, handoff_log = shapes[0]
+        for layer in range(n_split):
+            subs = torch.zeros((world, 32), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            for r, c in enumerate(ctxs):
+                c.fri_split_layer(layer, subs[r].data_ptr())
+            torch.cuda.synchronize()
+            for c in ctxs:
+                c.fri_split_combine(layer, subs.data_ptr())
+            torch.cuda.synchronize()
+        cols = torch.zeros((world, 4 << handoff_log), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for r, c in enumerate(ctxs):
+            c.fri_split_handoff(cols[r].data_ptr())
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.fri_split_finish(cols.data_ptr(), n_layers, cfg[1])
+        return [c.fri_split_decommit() for c in ctxs]
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("kind,n_bytes,seed,cfg,worlds", [
+    ("splitmix", 1 << 20, 11, (2, 0, 20, 12), (1, 2, 8)),      # poly_log 17
+    ("splitmix", 131072, 3, (4, 0, 64, 16), (2, 4, 16)),       # C4 shape: 64 queries
+    ("blob", 262146, None, (4, 1, 20, 20), (4,)),              # the reference's blob and config
+    ("splitmix", 131072, 9, (4, 5, 20, 8), (1, 2)),            # every committed layer split (world 1)
+    ("pattern", 40000, 5, (3, 1, 200, 6), (2, 8)),             # many queries: most tree paths merge early
+    ("splitmix", 8 << 20, None, (2, 0, 20, 12), (8,)),         # poly_log 20
+])
+def test_prove_split_virtual_ranks_byte_exact(torch_mod, blob_bytes, kind, n_bytes, seed, cfg, worlds):
+    # owner-serves-path decommitment: the merged proof must be the oracle's proof, byte for byte
+    from frieda_b200 import api
+    data = blob_bytes if kind == "blob" else case_data(kind, n_bytes)
+    oroot, opr = O.prove(data, seed, O.make_config(*cfg))
+    want = opr.serialize()
+    for world in worlds:
+        shares = split_prove_virtual(torch_mod, data, seed, cfg, world)
+        proof = api.split_assemble(shares)
+        assert proof.first_layer_commitment == oroot, world
+        assert proof.serialize() == want, world
+        assert F.verify_proof(proof, seed) and not F.verify_proof(proof, (seed or 0) + 1)
+        if world > 1:
+            # shares that do not belong together are refused, not merged into a wrong proof
+            with pytest.raises(F.FriedaError):
+                api.split_assemble(shares[::-1])
+            with pytest.raises(F.FriedaError):
+                api.split_assemble(shares[:-1] + [shares[-1][:-32]])
+            with pytest.raises(F.FriedaError):
+                api.split_assemble(shares[: world // 2])
+
+
+def test_prove_split_driver_single_rank(ctx):
+    from frieda_b200.parallel import prove_split
+    data = O.splitmix64_bytes(0x4652494544414236, 300000)
+    cfg = (3, 0, 20, 8)
+    root, proof = prove_split(ctx, data, 21, F.PcsConfig(*cfg))
+    oroot, opr = O.prove(data, 21, O.make_config(*cfg))
+    assert root == oroot and proof.serialize() == opr.serialize()
+    with pytest.raises(F.FriedaError):   # no kept trees: nothing to decommit from
+        ctx.fri_split_begin(data, None, F.PcsConfig(*cfg), 0, 1)
+        ctx.fri_split_decommit()
+
+
 def test_fri_commit_split_driver_single_rank_and_errors(ctx):
     from frieda_b200.parallel import fri_commit_split
     data = O.splitmix64_bytes(0x4652494544414236, 300000)

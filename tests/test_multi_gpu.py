@@ -36,6 +36,13 @@ for n_bytes, cfg, seed in ((1 << 20, (2, 0, 20, 12), 7), (131072, (4, 0, 20, 20)
     oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
     assert [r.tobytes() for r in roots] == oroots, (n_bytes, cfg)
     assert [tuple(int(x) for x in q) for q in last] == olast, (n_bytes, cfg)
+# ... and the whole proof: replicated grind + queries, owner-serves-path decommitment, shares all-gathered and merged
+for n_bytes, cfg, seed in ((1 << 20, (2, 0, 20, 12), 7), (131072, (4, 0, 64, 16), 5)):
+    data = O.splitmix64_bytes(0x4652494544414236 + n_bytes, n_bytes)
+    root, proof = parallel.prove_split(ctx, data, seed, F.PcsConfig(*cfg))
+    oroot, opr = O.prove(data, seed, O.make_config(*cfg))
+    assert root == oroot and proof.serialize() == opr.serialize(), (n_bytes, cfg)
+    assert F.verify_proof(proof, seed)
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTI_GPU_OK")

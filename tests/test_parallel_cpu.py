@@ -98,7 +98,7 @@ class _OracleSplitCtx:
     device = 0
     MIN_LOG = 10  # csrc/ctx.cu: SPLIT_MIN_LOG
 
-    def fri_split_begin(self, data, seed, cfg, rank, world):
+    def fri_split_begin(self, data, seed, cfg, rank, world, keep_trees=False):
         self.t = O.trace(bytes(data), seed, O.make_config(cfg.log_blowup_factor, cfg.log_last_layer_degree_bound,
                                                           cfg.n_queries, cfg.pow_bits), stop_after_fri=True, with_trees=True)
         self.rank, self.world, self.gl = rank, world, world.bit_length() - 1
