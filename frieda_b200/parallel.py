@@ -181,7 +181,26 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
             return out
-    n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
+    full = None
+    if on_gpu and world > 1 and distributed and all_gather is None:
+        # every rank needs the whole blob: each uploads 1/world of it over its own PCIe link, NCCL all-gathers the
+        # slices over NVLink (as commit_split's NCCL form does), and the library starts from device memory
+        import numpy as np
+        host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        host = host.reshape(-1).view(np.uint8)
+        per = slice_bounds(host.size, 0, world)[1]
+        if per >= (1 << 16):
+            with scope:
+                full = torch.empty(per * world, dtype=torch.uint8, device=dev)
+                lo, hi = slice_bounds(host.size, rank, world)
+                mine = torch.zeros(per, dtype=torch.uint8, device=dev)
+                if hi > lo:
+                    mine[: hi - lo].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
+                dist.all_gather_into_tensor(full, mine, group=group)
+            n_split, n_layers, handoff_log = ctx.fri_split_begin(None, seed, cfg, rank, world, device_ptr=full.data_ptr(),
+                                                                 length=host.size, keep_trees=keep_trees)
+    if full is None:
+        n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
     with scope:
         # (allocated inside the scope: every tensor the library writes is touched on the context's stream only)
         sub = torch.empty(32, dtype=torch.uint8, device=dev)
