@@ -128,10 +128,13 @@ struct frieda_ctx {
   // by frieda_ctx_take_error (the host-buffer entry points use a flag inside the wave's workspace instead)
   int *d_async_err() const { return reinterpret_cast<int *>(d_scratch + 4096 + 64); }
   // grow-only buffers of the proof path: gathered witnesses on the device, pinned readback on the host
-  uint8_t *d_gather = nullptr;
-  size_t d_gather_bytes = 0;
-  uint8_t *h_pinned[2] = {nullptr, nullptr};  // double-buffered: wave i is assembled while wave i+1 computes
+  // (both double-buffered: wave i is read back on the copy stream and assembled while wave i+1 computes)
+  uint8_t *d_gather[2] = {nullptr, nullptr};
+  size_t d_gather_bytes[2] = {0, 0};
+  uint8_t *h_pinned[2] = {nullptr, nullptr};
   size_t h_pinned_bytes[2] = {0, 0};
+  cudaEvent_t ev_gathered[2] = {nullptr, nullptr};  // wave's witnesses are in d_gather[b], small results read back
+  cudaEvent_t ev_readback[2] = {nullptr, nullptr};  // d_gather[b] has reached h_pinned[b]
   // per-kernel timing with CUDA events on the launching stream (bench.py's roofline)
   bool profiling = false;
   struct ProfRec {
@@ -651,17 +654,17 @@ int fri_commit_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t st
   return FRIEDA_OK;
 }
 
-int ensure_gather(frieda_ctx *ctx, size_t bytes) {
-  if (ctx->d_gather_bytes >= bytes) return FRIEDA_OK;
-  if (ctx->d_gather) {
+int ensure_gather(frieda_ctx *ctx, int idx, size_t bytes) {
+  if (ctx->d_gather_bytes[idx] >= bytes) return FRIEDA_OK;
+  if (ctx->d_gather[idx]) {
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_gather);
-    ctx->d_gather = nullptr;
-    ctx->d_gather_bytes = 0;
+    cudaFree(ctx->d_gather[idx]);
+    ctx->d_gather[idx] = nullptr;
+    ctx->d_gather_bytes[idx] = 0;
   }
   size_t want = bytes + bytes / 4 + 4096;
-  CU(cudaMalloc(&ctx->d_gather, want));
-  ctx->d_gather_bytes = want;
+  CU(cudaMalloc(&ctx->d_gather[idx], want));
+  ctx->d_gather_bytes[idx] = want;
   return FRIEDA_OK;
 }
 int ensure_pinned(frieda_ctx *ctx, int idx, size_t bytes) {
@@ -679,12 +682,13 @@ int ensure_pinned(frieda_ctx *ctx, int idx, size_t bytes) {
 
 // Host copy of one proof wave's results; two of them alternate so that the Proof objects of wave i are
 // assembled on host threads while the GPU already works on wave i + 1.
-struct ProveHostBuf {
-  std::vector<uint8_t> roots;
-  std::vector<frieda_qm31> last, evals;
-  std::vector<uint32_t> counts, nuniq;
-  std::vector<unsigned long long> offsets, best;
-  const uint8_t *fri = nullptr, *hash = nullptr;  // into the pinned readback buffer
+struct ProveHostBuf {  // every pointer into the wave's pinned readback buffer
+  const uint8_t *roots = nullptr;
+  const frieda_qm31 *last = nullptr, *evals = nullptr;
+  const uint32_t *counts = nullptr, *nuniq = nullptr;
+  const unsigned long long *offsets = nullptr, *best = nullptr;
+  const int *err_flag = nullptr;
+  const uint8_t *fri = nullptr, *hash = nullptr;
 };
 
 // Assembles the frieda_proof objects of blobs [b0, b0 + nb) (src/proof.rs:67-76).  Returns false on OOM.
@@ -778,11 +782,16 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
   const Geom &g = pl.g;
   const uint32_t L = g.n_layers;
   ProveHostBuf hbuf[2];
-  // background assembly of the previous wave; joined before its buffer is reused and on every exit path
+  // Waves are pipelined three ways: the NEXT wave's input is uploaded on the copy stream while this one computes; this
+  // wave's gathered witnesses (the bulk of a proof: ~130 KB at 64 queries) go back on the copy stream while the next
+  // wave computes; and a host thread turns them into Proof objects meanwhile.  The last (or only) wave does its
+  // readback on the compute stream and is assembled by the calling thread: a single small proof pays for no thread
+  // and no cross-stream hop.
+  enum { W_OK = 0, W_OOM = 1, W_DEGREE = 2, W_POW = 3, W_CUDA = 4 };
   struct Workers {
     std::thread th[2];
     bool active[2] = {false, false};
-    std::atomic<bool> failed{false};
+    std::atomic<int> failed{W_OK};
     void join(int i) {
       if (active[i]) {
         th[i].join();
@@ -794,29 +803,64 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
       join(1);
     }
   } workers;
+  // checks a wave's flags and assembles its proofs; runs on the calling thread or on a worker
+  auto finish_wave = [&workers, &g, nq, cfg, roots_out, proofs_out](const ProveHostBuf &hb, size_t b0, size_t nb) {
+    if (*hb.err_flag) {
+      workers.failed = W_DEGREE;
+      return;
+    }
+    for (size_t b = 0; b < nb; b++)
+      if (hb.best[b] == ~0ull) {
+        workers.failed = W_POW;
+        return;
+      }
+    if (!assemble_wave(hb, b0, nb, g, nq, cfg, roots_out, proofs_out)) workers.failed = W_OOM;
+  };
+  auto fail_code = [&]() -> int {
+    workers.join(0);
+    workers.join(1);
+    const int f = workers.failed;
+    if (f == W_OK) return FRIEDA_OK;
+    for (size_t i = 0; i < n; i++) {  // a failed call returns no proofs
+      if (proofs_out[i]) frieda_proof_free(proofs_out[i]);
+      proofs_out[i] = nullptr;
+    }
+    if (f == W_DEGREE) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
+    if (f == W_POW) return ctx->fail_arg("proof of work search exhausted");
+    if (f == W_CUDA) return ctx->fail_arg("proof readback failed on the copy stream", FRIEDA_ERR_CUDA);
+    return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
+  };
   CU(cudaMemsetAsync(at<int>(ctx, pl.o_err), 0, sizeof(int), ctx->stream));
+  // uploads run on the copy stream, one wave ahead of compute
+  CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+  CU(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+  if ((rc = stage_upload(ctx, pl, 0, blobs, stride, std::min(B, n)))) return rc;
   size_t wave_index = 0;
   for (size_t b0 = 0; b0 < n; b0 += B, wave_index++) {
     size_t nb = std::min(B, n - b0);
     const int bi = (int)(wave_index & 1);
+    const bool last_wave = b0 + B >= n;
     ProveHostBuf &hb = hbuf[bi];
     Plan w = pl;
     w.B = nb;
     const uint8_t *d_in;
     size_t d_stride;
     const uint64_t *d_seeds = nullptr;
-    if ((rc = stage_in(ctx, w, blobs + b0 * stride, stride, &d_in, &d_stride))) return rc;
+    if (!last_wave &&
+        (rc = stage_upload(ctx, pl, bi ^ 1, blobs + (b0 + B) * stride, stride, std::min(B, n - b0 - B))))
+      return rc;
+    if ((rc = stage_acquire(ctx, pl, bi, &d_in, &d_stride))) return rc;
     if (seeds) {
       CU(cudaMemcpyAsync(at<uint64_t>(ctx, w.o_seeds), seeds + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
       d_seeds = at<uint64_t>(ctx, w.o_seeds);
     }
-    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds))) return rc;
+    if ((rc = fri_wave(ctx, w, d_in, d_stride, d_seeds, bi))) return rc;
     tr.mark("fri launches");
-    // proof of work (src/proof.rs:58): rounds of 2^22 nonces until every blob has its minimum
+    // proof of work (src/proof.rs:58): every blob's minimum nonce, no host round trip
     Channel *chan = at<Channel>(ctx, w.o_chan);
     unsigned long long *best = at<unsigned long long>(ctx, w.o_best);
     CU(cudaMemsetAsync(best, 0xff, nb * 8, ctx->stream));
-    // enough CTAs to fill the GPU when the wave is small, 64 per blob otherwise
+    // enough CTAs to fill the GPU when the wave is small, 32 per blob otherwise
     uint32_t ctas = 32;
     while ((size_t)ctas * nb < 2368 && ctas < 2048) ctas <<= 1;
     const uint64_t limit = (uint64_t)1 << (cfg->pow_bits + 12 > 62 ? 62 : cfg->pow_bits + 12);
@@ -851,13 +895,20 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     tr.mark("grind+decommit launches");
     CU(cudaStreamSynchronize(ctx->stream));
     tr.mark("sync 1 (fri+grind+count)");
-    // gathered witnesses live in a separate allocation sized by the exact totals
-    size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
+    // gathered witnesses live in a separate allocation sized by the exact totals; the readback buffer holds the
+    // small per-blob results first, then the witnesses
+    const size_t fri_bytes = (size_t)totals[0] * sizeof(QM31), hash_bytes = (size_t)totals[1] * 32;
     const size_t fri_pad = align_up(fri_bytes, 256);
-    if ((rc = ensure_gather(ctx, fri_pad + hash_bytes + 256))) return rc;
-    workers.join(bi);  // the wave that used this host buffer two iterations ago is assembled
-    if ((rc = ensure_pinned(ctx, bi, fri_pad + hash_bytes + 256))) return rc;
-    uint8_t *d_gather = ctx->d_gather;
+    Bump hp;
+    const size_t h_roots = hp.take(nb * L * 32), h_last = hp.take((nb * sizeof(frieda_qm31)) << g.log_last);
+    const size_t h_evals = hp.take(nb * nq * sizeof(frieda_qm31)), h_counts = hp.take(nb * L * 2 * 4);
+    const size_t h_offsets = hp.take(nb * L * 2 * 8), h_nuniq = hp.take(nb * 4), h_best = hp.take(nb * 8);
+    const size_t h_err = hp.take(sizeof(int)), h_wit = hp.take(fri_pad + hash_bytes + 256);
+    workers.join(bi);  // the wave that used these buffers two iterations ago is read back and assembled
+    if (workers.failed) return fail_code();
+    if ((rc = ensure_gather(ctx, bi, fri_pad + hash_bytes + 256))) return rc;
+    if ((rc = ensure_pinned(ctx, bi, hp.off))) return rc;
+    uint8_t *d_gather = ctx->d_gather[bi], *hpin = ctx->h_pinned[bi];
     dp.fri_out = reinterpret_cast<QM31 *>(d_gather);
     dp.hash_out = d_gather + fri_pad;
     ctx->prof_begin("decommit_write");
@@ -865,53 +916,58 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     ctx->prof_end();
     if (le != cudaSuccess) return ctx->fail(le, "launch_decommit_write", __LINE__);
     ctx->launches += 2;
-    hb.roots.resize(nb * L * 32);
-    hb.last.resize(nb << g.log_last);
-    hb.evals.resize(nb * nq);
-    hb.counts.resize(nb * L * 2);
-    hb.offsets.resize(nb * L * 2);
-    hb.nuniq.resize(nb);
-    hb.best.resize(nb);
-    int err_flag = 0;
     cudaError_t ce = cudaSuccess;
-    auto cp = [&](void *dst, const void *src, size_t bytes) {
-      if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    auto cp = [&](size_t h_off, const void *src, size_t bytes, cudaStream_t st) {
+      if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(hpin + h_off, src, bytes, cudaMemcpyDeviceToHost, st);
     };
-    cp(hb.roots.data(), at<uint8_t>(ctx, w.o_roots), hb.roots.size());
-    cp(hb.last.data(), at<QM31>(ctx, w.o_last), hb.last.size() * sizeof(frieda_qm31));
-    cp(hb.evals.data(), dp.evals_out, hb.evals.size() * sizeof(frieda_qm31));
-    cp(hb.counts.data(), dp.counts, hb.counts.size() * 4);
-    cp(hb.offsets.data(), dp.offsets, hb.offsets.size() * 8);
-    cp(hb.nuniq.data(), nuniq, nb * 4);
-    cp(hb.best.data(), best, nb * 8);
-    cp(ctx->h_pinned[bi], d_gather, fri_pad + hash_bytes);  // witnesses: one copy into pinned memory
-    hb.fri = ctx->h_pinned[bi];
-    hb.hash = ctx->h_pinned[bi] + fri_pad;
-    cp(&err_flag, at<int>(ctx, w.o_err), sizeof(int));
-    tr.mark("write launch + readback enqueue");
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    tr.mark("sync 2 (write+d2h)");
-    if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
-    if (err_flag) return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);
-    for (size_t b = 0; b < nb; b++)
-      if (hb.best[b] == ~0ull) return ctx->fail_arg("proof of work search exhausted");
-    // assemble this wave's Proof objects in the background while the next wave computes
-    if (b0 + B < n) {
-      workers.th[bi] = std::thread([&workers, &hb, b0, nb, &g, nq, cfg, roots_out, proofs_out]() {
-        if (!assemble_wave(hb, b0, nb, g, nq, cfg, roots_out, proofs_out)) workers.failed = true;
+    cp(h_roots, at<uint8_t>(ctx, w.o_roots), nb * L * 32, ctx->stream);
+    cp(h_last, at<QM31>(ctx, w.o_last), (nb * sizeof(frieda_qm31)) << g.log_last, ctx->stream);
+    cp(h_evals, dp.evals_out, nb * nq * sizeof(frieda_qm31), ctx->stream);
+    cp(h_counts, dp.counts, nb * L * 2 * 4, ctx->stream);
+    cp(h_offsets, dp.offsets, nb * L * 2 * 8, ctx->stream);
+    cp(h_nuniq, nuniq, nb * 4, ctx->stream);
+    cp(h_best, best, nb * 8, ctx->stream);
+    cp(h_err, at<int>(ctx, w.o_err), sizeof(int), ctx->stream);
+    hb.roots = hpin + h_roots;
+    hb.last = reinterpret_cast<const frieda_qm31 *>(hpin + h_last);
+    hb.evals = reinterpret_cast<const frieda_qm31 *>(hpin + h_evals);
+    hb.counts = reinterpret_cast<const uint32_t *>(hpin + h_counts);
+    hb.offsets = reinterpret_cast<const unsigned long long *>(hpin + h_offsets);
+    hb.nuniq = reinterpret_cast<const uint32_t *>(hpin + h_nuniq);
+    hb.best = reinterpret_cast<const unsigned long long *>(hpin + h_best);
+    hb.err_flag = reinterpret_cast<const int *>(hpin + h_err);
+    hb.fri = hpin + h_wit;
+    hb.hash = hpin + h_wit + fri_pad;
+    if (last_wave) {
+      cp(h_wit, d_gather, fri_pad + hash_bytes, ctx->stream);
+      tr.mark("write launch + readback enqueue");
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+      tr.mark("sync 2 (write+d2h)");
+      if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
+      finish_wave(hb, b0, nb);
+      tr.mark("assemble");
+    } else {
+      // witnesses go back on the copy stream, behind the next wave's upload and under its compute
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_gathered[bi], ctx->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gathered[bi], 0);
+      cp(h_wit, d_gather, fri_pad + hash_bytes, ctx->copy_stream);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_readback[bi], ctx->copy_stream);
+      if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
+      cudaEvent_t ev = ctx->ev_readback[bi];
+      const int device = ctx->device;
+      workers.th[bi] = std::thread([&workers, finish_wave, &hb, ev, device, b0, nb]() {
+        if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(ev) != cudaSuccess) {
+          workers.failed = W_CUDA;
+          return;
+        }
+        finish_wave(hb, b0, nb);
       });
       workers.active[bi] = true;
-    } else if (!assemble_wave(hb, b0, nb, g, nq, cfg, roots_out, proofs_out)) {
-      workers.failed = true;
     }
-    tr.mark("assemble");
     ctx->last = w;
     ctx->have_last = true;
   }
-  workers.join(0);
-  workers.join(1);
-  if (workers.failed) return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
-  return FRIEDA_OK;
+  return fail_code();
 }
 
 }  // namespace
@@ -943,6 +999,10 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_free[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_gathered[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_gathered[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_readback[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_readback[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_scratch, 8192)) != cudaSuccess ||
       (e = cudaMemset(ctx->d_scratch, 0, 8192)) != cudaSuccess) {
     g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e);
@@ -972,9 +1032,12 @@ void frieda_ctx_destroy(frieda_ctx *ctx) {
   cudaFree(ctx->d_tw2);
   cudaFree(ctx->arena);
   cudaFree(ctx->d_scratch);
-  cudaFree(ctx->d_gather);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
+    cudaFree(ctx->d_gather[i]);
     if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
+    if (ctx->ev_gathered[i]) cudaEventDestroy(ctx->ev_gathered[i]);
+    if (ctx->ev_readback[i]) cudaEventDestroy(ctx->ev_readback[i]);
+  }
   for (auto &r : ctx->prof_recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -1706,9 +1769,9 @@ int frieda_fri_split_decommit(frieda_ctx *ctx, uint8_t **share_out, size_t *shar
   }
   const size_t dq_bytes = align_up(gq.size() * sizeof(GatherQ) + 16, 256), dh_bytes = align_up(gh.size() * sizeof(GatherH) + 16, 256);
   const size_t oq_bytes = align_up(gq.size() * 16 + 16, 256), oh_bytes = gh.size() * 32 + 32;
-  int rc = ensure_gather(ctx, dq_bytes + dh_bytes + oq_bytes + oh_bytes);
+  int rc = ensure_gather(ctx, 0, dq_bytes + dh_bytes + oq_bytes + oh_bytes);
   if (rc) return rc;
-  uint8_t *d = ctx->d_gather;
+  uint8_t *d = ctx->d_gather[0];
   if (!gq.empty()) CU(cudaMemcpyAsync(d, gq.data(), gq.size() * sizeof(GatherQ), cudaMemcpyHostToDevice, ctx->stream));
   if (!gh.empty()) CU(cudaMemcpyAsync(d + dq_bytes, gh.data(), gh.size() * sizeof(GatherH), cudaMemcpyHostToDevice, ctx->stream));
   KL("gather_items", launch_gather_items(ctx->stream, reinterpret_cast<const GatherQ *>(d), (uint32_t)gq.size(),
