@@ -84,9 +84,25 @@ uint32_t layer_log(const Geom &g, uint32_t layer) { return g.D - layer; }
 // Levels reduced inside one CTA of the Merkle bottom/middle passes.  Deep (10: 1024 leaves -> 1
 // node) minimises launches but parks most warps at barriers during the last 8 levels; shallow
 // (2: 1024 -> 256) keeps every thread hashing in every level at the cost of more passes.
-uint32_t pass_levels(uint32_t d, uint32_t levels_cfg) {
+// levels_cfg: bits 0-7 = levels per pass.  LV_LATENCY (a few blobs have the GPU to themselves: the tree is a chain of
+// dependent compressions, not a throughput problem) selects the latency form of the Merkle passes (merkle.cu) and
+// chunks small enough that the bottom pass leaves about 2^t nodes per blob (bits 16-23 = t), i.e. roughly one CTA
+// per SM over the blobs of the call.
+constexpr uint32_t LV_LATENCY = 0x100;
+uint32_t lv_levels(uint32_t levels_cfg) { return levels_cfg & 0xffu; }
+uint32_t chunk_log_for(uint32_t d, uint32_t levels_cfg) {
   uint32_t chunk = d < 10 ? d : 10;
-  return levels_cfg < chunk ? levels_cfg : chunk;
+  if (levels_cfg & LV_LATENCY) {
+    const uint32_t t = (levels_cfg >> 16) & 0xffu;
+    uint32_t c = d > t ? d - t : 0;
+    if (c < 7) c = 7;
+    if (c < chunk) chunk = c;
+  }
+  return chunk;
+}
+uint32_t pass_levels(uint32_t d, uint32_t levels_cfg) {
+  const uint32_t chunk = chunk_log_for(d, levels_cfg), lv = lv_levels(levels_cfg);
+  return lv < chunk ? lv : chunk;
 }
 size_t tree_slots(uint32_t d, bool keep, uint32_t levels_cfg) {
   // kept trees hold every level; truncated trees only the levels above the bottom pass
@@ -109,10 +125,17 @@ struct frieda_ctx {
   size_t ws_limit = 0;
   uint32_t merkle_levels_big = 3;    // per-pass depth for large batches (env FRIEDA_MERKLE_LEVELS)
   uint32_t merkle_levels_small = 10; // per-pass depth when the grid would not fill the GPU anyway
+  uint32_t merkle_latency_max_chunk = 8;  // (env FRIEDA_MERKLE_LATENCY_CHUNK, for probing)
+  bool merkle_latency_form = true;   // latency form of the Merkle passes for those calls (env FRIEDA_MERKLE_LATENCY=0: off)
   uint32_t levels_for(size_t n_blobs, uint32_t d) const {
     // CTAs of the bottom pass; below ~4 waves of 148 SMs x 4 CTAs the launch count matters more
     size_t ctas = n_blobs << (d > 10 ? d - 10 : 0);
-    return ctas >= 2368 ? merkle_levels_big : merkle_levels_small;
+    if (ctas >= 2368) return merkle_levels_big;
+    if (merkle_levels_small != 10 || !merkle_latency_form) return merkle_levels_small;
+    uint32_t lg = 0;  // floor(log2(n_blobs))
+    while ((n_blobs >> (lg + 1)) != 0) lg++;
+    const uint32_t t = lg >= 7 ? 0 : 7 - lg;
+    return merkle_levels_small | 0x100u /* LV_LATENCY */ | (t << 16);
   }
   // twiddle cache
   bool tw_valid = false;
@@ -387,10 +410,13 @@ T *at(frieda_ctx *ctx, size_t off) {
 int run_tree(frieda_ctx *ctx, int src, MerkleBottomParams mp, uint32_t d, uint32_t levels_cfg, bool keep,
              size_t n_blobs, uint8_t *roots, size_t roots_stride, Channel *chan, QM31 *alpha, size_t alpha_stride) {
   mp.log = d;
-  mp.chunk_log = d < 10 ? d : 10;
+  mp.chunk_log = chunk_log_for(d, levels_cfg);
   mp.levels = pass_levels(d, levels_cfg);
   mp.src_level = d;
   mp.write_all = keep ? 1 : 0;
+  // the 128-thread latency form pays off for chunks of <= 256 leaves (one or two leaves per thread); larger chunks
+  // keep the 256-thread form, whose second warp per scheduler hides the latency of the column loads
+  mp.latency = ((levels_cfg & LV_LATENCY) && mp.chunk_log <= ctx->merkle_latency_max_chunk) ? 1 : 0;
   KL(src == SRC_COLS ? "merkle_bottom_cols" : src == SRC_FOLD_CIRCLE ? "fold_circle+merkle_bottom" : "fold_line+merkle_bottom",
      launch_merkle_bottom(ctx->stream, src, mp, n_blobs), 1);
   uint32_t u = d - mp.levels;
@@ -402,10 +428,11 @@ int run_tree(frieda_ctx *ctx, int src, MerkleBottomParams mp, uint32_t d, uint32
     mm.log = u;
     mm.src_level = u;
     mm.chunk_log = 10;
+    mm.latency = 0;
     // shallow passes keep every thread hashing, but only pay off while the pass still fills the GPU: with fewer than
     // ~4 waves of CTAs (one big tree: config 5) a pass is latency-bound and fewer, deeper passes are faster
     const size_t ctas = n_blobs << (u - 10);
-    mm.levels = (levels_cfg < 10 && ctas >= 2368) ? levels_cfg : 10;
+    mm.levels = (lv_levels(levels_cfg) < 10 && ctas >= 2368) ? lv_levels(levels_cfg) : 10;
     if (mm.levels > u - 10) mm.levels = u - 10;  // stop exactly where the top kernel takes over
     KL("merkle_mid", launch_merkle_bottom(ctx->stream, SRC_NODES, mm, n_blobs), 1);
     u -= mm.levels;
@@ -1014,6 +1041,8 @@ int frieda_ctx_create(int device, frieda_ctx **out) {
     int v = std::atoi(ev);
     if (v >= 1 && v <= 10) ctx->merkle_levels_big = (uint32_t)v;
   }
+  if (const char *ev = std::getenv("FRIEDA_MERKLE_LATENCY")) ctx->merkle_latency_form = std::atoi(ev) != 0;
+  if (const char *ev = std::getenv("FRIEDA_MERKLE_LATENCY_CHUNK")) ctx->merkle_latency_max_chunk = (uint32_t)std::atoi(ev);
   CPoint cur = {host::GEN_X, host::GEN_Y};
   for (int j = 0; j < 31; j++) {
     ctx->gp.g[j] = cur;

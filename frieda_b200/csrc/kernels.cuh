@@ -52,6 +52,7 @@ struct MerkleBottomParams {
   uint32_t levels;           // levels reduced inside the CTA (<= chunk_log)
   uint32_t src_level;        // SRC_NODES: tree level the 2^log input nodes live on; others: == log
   int write_all;             // write every level (leaves included) to the tree, not only the tops
+  int latency;               // latency form (merkle.cu): 128-thread CTAs, chunks of <= 256 leaves
   uint32_t one;              // runtime 1 for the IMAD adds of the compression (blake2s.cuh); set by the launcher
 };
 

@@ -18,7 +18,8 @@
 
 namespace frieda {
 
-constexpr int MB_THREADS = 256;
+constexpr int MB_THREADS = 256;      // throughput form: batches, big trees, and 512+ leaves per CTA
+constexpr int MB_THREADS_LAT = 128;  // latency form (see MbOccupancy)
 constexpr uint32_t MB_CHUNK_LOG_MAX = 10;  // 1024 leaves -> 32 KiB of shared memory (levels are reduced in place)
 
 struct alignas(16) Hash32 {
@@ -55,9 +56,17 @@ __device__ __forceinline__ uint32_t circle_fold_itw(const uint32_t *iblk, size_t
 // Levels are reduced in place: all threads finish hashing a level before anyone overwrites it.
 // Resident CTAs per SM (measured, one FRI-commit wave of 1024 blobs): leaves-from-columns 20.09 / 19.50 / 18.84 ms
 // at 4 / 5 / 6; the fold variants 11.1 / 10.3 / 10.6 ms (the fold's 4x4 matrix wants the registers).
-template <int SRC>
+// Latency form (T = 128, chunks of <= 256 leaves): one blob (or a few) has the GPU to itself, so a tree is a chain of
+// dependent compressions (0.85 - 0.93 us per link with one warp per scheduler, 1.76 us with two:
+// bench_micro/chain.cu), not a throughput problem.  The host picks chunks small enough that about one CTA lands on
+// every SM (ctx.cu: chunk_log_for); ptxas places the adds itself (8 % faster per dependent compression than the
+// all-IMAD form) and is not held to a register budget.  Measured on one 128 KiB blob (FRI commit, 9 trees):
+// 0.489 -> 0.439 ms.  Letting the CTA that finishes last (a ticket per blob) also reduce the tops and run the
+// transcript step, instead of launching merkle_top_kernel, was built and measured: no gain (the fences and the
+// ticket cost what the launch gap does), so the top stays a kernel of its own.
+template <int SRC, int T>
 struct MbOccupancy {
-  static constexpr int min_blocks = SRC == SRC_COLS ? 6 : 5;
+  static constexpr int min_blocks = T == MB_THREADS_LAT ? 1 : (SRC == SRC_COLS ? 6 : 5);
 };
 constexpr uint32_t MB2_HALF = 1u << (MB_CHUNK_LOG_MAX - 1);
 __device__ __forceinline__ uint32_t *mb2_word(uint32_t *sm, uint32_t node, uint32_t s) {
@@ -73,18 +82,68 @@ __device__ __forceinline__ void mb2_put(uint32_t *sm, uint32_t node, const uint3
   for (int s = 0; s < 8; s++) *mb2_word(sm, node, s) = h[s];
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(MB_THREADS, MbOccupancy<SRC>::min_blocks) merkle_bottom_kernel(const MerkleBottomParams p) {
+// Reduces `levels` levels of the cnt nodes held in the level buffer (in place); the nodes sit on tree level `level`
+// at index idx0 + j.  Stores every level (write_all) or only the last one into the tree.
+template <int T>
+__device__ __forceinline__ void mb2_reduce(uint32_t *sm, uint32_t cnt, uint32_t levels, uint32_t level, size_t idx0,
+                                           Hash32 *tree, int write_all, uint32_t one) {
+  for (uint32_t l = 0; l < levels; l++) {
+    cnt >>= 1;
+    level -= 1;
+    idx0 >>= 1;
+    const bool top = (l + 1 == levels);
+    Hash32 *out = tree + ((size_t)1 << level) + idx0;
+    if (T == MB_THREADS) {
+      // cnt <= 512: at most two nodes per thread, both digests held across ONE barrier (every compression of the
+      // level has read its children before anyone overwrites them).  Holding only the first and hashing the second
+      // after the barrier removes the spills of this form but measured 4.5 % slower end to end.
+      const uint32_t j0 = threadIdx.x, j1 = threadIdx.x + T;
+      uint32_t h0[8], h1[8];
+      if (j0 < cnt) merkle_hash_node_msg(Mb2PairMsg{sm + j0, sm + 8 * MB2_HALF + 16 + j0}, h0, one);
+      if (j1 < cnt) merkle_hash_node_msg(Mb2PairMsg{sm + j1, sm + 8 * MB2_HALF + 16 + j1}, h1, one);
+      __syncthreads();
+      if (j0 < cnt) {
+        if (!top) mb2_put(sm, j0, h0);
+        if (write_all || top) store_hash(out + j0, h0);
+      }
+      if (j1 < cnt) {
+        if (!top) mb2_put(sm, j1, h1);
+        if (write_all || top) store_hash(out + j1, h1);
+      }
+    } else {
+      // rounds of T nodes: node j reads slots j of the even / odd halves and is stored to slot j >> 1.  An EVEN round
+      // holds its digest (one per thread) across a barrier, because its stores land on slots that the round itself
+      // (round 0) or the previous round still reads; an ODD round r stores at once: its slots [rT/2, (r+1)T/2) were
+      // read in rounds < r, which every warp has left at the last barrier.
+      for (uint32_t r = 0, j0 = 0; j0 < cnt; r++, j0 += T) {
+        const uint32_t j = j0 + threadIdx.x;
+        uint32_t h[8];
+        if (j < cnt) merkle_hash_node_msg(Mb2PairMsg{sm + j, sm + 8 * MB2_HALF + 16 + j}, h, one);
+        if ((r & 1u) == 0) __syncthreads();
+        if (j < cnt) {
+          if (!top) mb2_put(sm, j, h);
+          if (write_all || top) store_hash(out + j, h);
+        }
+      }
+    }
+    if (!top) __syncthreads();
+  }
+}
+
+template <int SRC, int T>
+__global__ void __launch_bounds__(T, MbOccupancy<SRC, T>::min_blocks) merkle_bottom_kernel(const MerkleBottomParams p) {
   __shared__ uint32_t sm[2 * 8 * MB2_HALF + 16];
   const size_t blob = blockIdx.y;
   const uint32_t chunk = blockIdx.x;
   const uint32_t n_chunk = 1u << p.chunk_log;
   const size_t leaf0 = (size_t)chunk << p.chunk_log;
   Hash32 *tree = reinterpret_cast<Hash32 *>(p.tree) + blob * p.tree_stride;
+  // the throughput form forces the adds onto the FMA pipe through the opaque runtime 1 (blake2s.cuh)
+  const uint32_t one = T == MB_THREADS_LAT ? 1u : p.one;
 
   if (SRC == SRC_NODES) {
     const Hash32 *src = tree + ((size_t)1 << p.src_level) + leaf0;
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += T) {
       const Hash32 v = src[j];
       const uint32_t h[8] = {v.lo.x, v.lo.y, v.lo.z, v.lo.w, v.hi.x, v.hi.y, v.hi.z, v.hi.w};
       mb2_put(sm, j, h);
@@ -93,7 +152,7 @@ __global__ void __launch_bounds__(MB_THREADS, MbOccupancy<SRC>::min_blocks) merk
     const size_t n = (size_t)1 << p.log;
     QM31Mat amat;
     if (SRC == SRC_FOLD_CIRCLE || SRC == SRC_FOLD_LINE) amat = qm31_mat(p.alpha[blob * p.alpha_stride]);
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += T) {
       const size_t i = leaf0 + j;
       uint32_t c0, c1, c2, c3;
       if (SRC == SRC_COLS) {
@@ -119,38 +178,17 @@ __global__ void __launch_bounds__(MB_THREADS, MbOccupancy<SRC>::min_blocks) merk
         d[3 * n] = c3;
       }
       uint32_t h[8];
-      merkle_hash_leaf(c0, c1, c2, c3, h, p.one);
+      merkle_hash_leaf(c0, c1, c2, c3, h, one);
       mb2_put(sm, j, h);
       if (p.write_all) store_hash(tree + n + i, h);
     }
   }
   __syncthreads();
-  uint32_t cnt = n_chunk;
-  uint32_t level = (SRC == SRC_NODES ? p.src_level : p.log);
-  size_t idx0 = leaf0;
-  for (uint32_t l = 0; l < p.levels; l++) {
-    cnt >>= 1;  // <= 512: at most two nodes per thread
-    level -= 1;
-    idx0 >>= 1;
-    const bool top = (l + 1 == p.levels);
-    const uint32_t j0 = threadIdx.x, j1 = threadIdx.x + MB_THREADS;
-    uint32_t h0[8], h1[8];
-    if (j0 < cnt) merkle_hash_node_msg(Mb2PairMsg{sm + j0, sm + 8 * MB2_HALF + 16 + j0}, h0, p.one);
-    if (j1 < cnt) merkle_hash_node_msg(Mb2PairMsg{sm + j1, sm + 8 * MB2_HALF + 16 + j1}, h1, p.one);
-    __syncthreads();  // every compression of this level has read its children
-    if (j0 < cnt) {
-      if (!top) mb2_put(sm, j0, h0);
-      if (p.write_all || top) store_hash(tree + ((size_t)1 << level) + idx0 + j0, h0);
-    }
-    if (j1 < cnt) {
-      if (!top) mb2_put(sm, j1, h1);
-      if (p.write_all || top) store_hash(tree + ((size_t)1 << level) + idx0 + j1, h1);
-    }
-    if (!top) __syncthreads();
-  }
+  const uint32_t level = (SRC == SRC_NODES ? p.src_level : p.log);
+  mb2_reduce<T>(sm, n_chunk, p.levels, level, leaf0, tree, p.write_all, one);
   if (p.levels == 0 && !p.write_all && SRC != SRC_NODES) {
     const size_t n = (size_t)1 << p.log;
-    for (uint32_t j = threadIdx.x; j < n_chunk; j += MB_THREADS) {
+    for (uint32_t j = threadIdx.x; j < n_chunk; j += T) {
       uint32_t h[8];
 #pragma unroll
       for (int s = 0; s < 8; s++) h[s] = *mb2_word(sm, j, s);
@@ -171,12 +209,24 @@ cudaError_t launch_merkle_bottom(cudaStream_t st, int src, const MerkleBottomPar
     q.tree += b0 * p.tree_stride * 32;
     if (q.alpha) q.alpha += b0 * p.alpha_stride;
     dim3 grid(chunks, (unsigned)nb);
-    switch (src) {
-      case SRC_COLS: merkle_bottom_kernel<SRC_COLS><<<grid, MB_THREADS, 0, st>>>(q); break;
-      case SRC_FOLD_CIRCLE: merkle_bottom_kernel<SRC_FOLD_CIRCLE><<<grid, MB_THREADS, 0, st>>>(q); break;
-      case SRC_FOLD_LINE: merkle_bottom_kernel<SRC_FOLD_LINE><<<grid, MB_THREADS, 0, st>>>(q); break;
-      case SRC_NODES: merkle_bottom_kernel<SRC_NODES><<<grid, MB_THREADS, 0, st>>>(q); break;
-      default: return cudaErrorInvalidValue;
+    if (p.latency) {
+      constexpr int T = MB_THREADS_LAT;
+      switch (src) {
+        case SRC_COLS: merkle_bottom_kernel<SRC_COLS, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_FOLD_CIRCLE: merkle_bottom_kernel<SRC_FOLD_CIRCLE, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_FOLD_LINE: merkle_bottom_kernel<SRC_FOLD_LINE, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_NODES: merkle_bottom_kernel<SRC_NODES, T><<<grid, T, 0, st>>>(q); break;
+        default: return cudaErrorInvalidValue;
+      }
+    } else {
+      constexpr int T = MB_THREADS;
+      switch (src) {
+        case SRC_COLS: merkle_bottom_kernel<SRC_COLS, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_FOLD_CIRCLE: merkle_bottom_kernel<SRC_FOLD_CIRCLE, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_FOLD_LINE: merkle_bottom_kernel<SRC_FOLD_LINE, T><<<grid, T, 0, st>>>(q); break;
+        case SRC_NODES: merkle_bottom_kernel<SRC_NODES, T><<<grid, T, 0, st>>>(q); break;
+        default: return cudaErrorInvalidValue;
+      }
     }
   }
   return cudaGetLastError();
