@@ -887,11 +887,8 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     Channel *chan = at<Channel>(ctx, w.o_chan);
     unsigned long long *best = at<unsigned long long>(ctx, w.o_best);
     CU(cudaMemsetAsync(best, 0xff, nb * 8, ctx->stream));
-    // enough CTAs to fill the GPU when the wave is small, 32 per blob otherwise
-    uint32_t ctas = 32;
-    while ((size_t)ctas * nb < 2368 && ctas < 2048) ctas <<= 1;
     const uint64_t limit = (uint64_t)1 << (cfg->pow_bits + 12 > 62 ? 62 : cfg->pow_bits + 12);
-    KL("grind", launch_grind(ctx->stream, chan, cfg->pow_bits, limit, ctas, best, at<unsigned long long>(ctx, w.o_next), nb), 1);
+    KL("grind", launch_grind(ctx->stream, chan, cfg->pow_bits, limit, best, at<unsigned long long>(ctx, w.o_next), nb), 1);
     // queries + decommitment (src/proof.rs:59-66)
     uint32_t *queries = at<uint32_t>(ctx, w.o_queries);
     uint32_t *nuniq = at<uint32_t>(ctx, w.o_nuniq);
@@ -1752,7 +1749,7 @@ int frieda_fri_split_decommit(frieda_ctx *ctx, uint8_t **share_out, size_t *shar
   unsigned long long *best = at<unsigned long long>(ctx, sp.o_best);
   CU(cudaMemsetAsync(best, 0xff, 8, ctx->stream));
   const uint64_t limit = (uint64_t)1 << (sp.cfg.pow_bits + 12 > 62 ? 62 : sp.cfg.pow_bits + 12);
-  KL("grind", launch_grind(ctx->stream, chan, sp.cfg.pow_bits, limit, 2048, best, at<unsigned long long>(ctx, sp.o_next), 1), 1);
+  KL("grind", launch_grind(ctx->stream, chan, sp.cfg.pow_bits, limit, best, at<unsigned long long>(ctx, sp.o_next), 1), 1);
   uint32_t *d_queries = at<uint32_t>(ctx, sp.o_queries), *d_nuniq = at<uint32_t>(ctx, sp.o_nuniq);
   KL("queries", launch_queries(ctx->stream, chan, best, g.D, nq, d_queries, d_nuniq, 1), 1);
   unsigned long long nonce = 0;

@@ -143,9 +143,9 @@ constexpr uint32_t TAIL_LAST_MAX = 9; // largest supported log_last + log_blowup
 cudaError_t launch_tail(cudaStream_t st, const TailParams &p, size_t n_blobs);
 
 // Proof of work: best[b] = min nonce in [0, limit) whose raw-compress mix has >= pow_bits trailing
-// zeros (atomicMin; initialise to ~0ull).  The warps of ctas_per_blob CTAs take nonce chunks of each
-// blob in increasing order from next[b] (zeroed here).
-cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t limit, uint32_t ctas_per_blob,
+// zeros (atomicMin; initialise to ~0ull).  The warps of up to 128 CTAs per blob (more for a handful of blobs) take
+// nonce chunks of their blob in increasing order from next[b] (zeroed here).
+cudaError_t launch_grind(cudaStream_t st, const Channel *chan, uint32_t pow_bits, uint64_t limit,
                          unsigned long long *best, unsigned long long *next, size_t n_blobs);
 // mix_u64(nonce) then Queries::generate: sorted unique positions per blob.
 cudaError_t launch_queries(cudaStream_t st, Channel *chan, const unsigned long long *nonce, uint32_t log_domain,
