@@ -435,7 +435,9 @@ def main():
                       "ms_resident": (round(c5["ms_per_blob_slices_resident"], 4)
                                       if c5.get("ms_per_blob_slices_resident") else None),
                       "exchange": c5["exchange_short"], "gb_per_s": round(c5["input_gb_per_s"], 2),
-                      "fri_ms": round(c5["fri_commit_split_ms"], 3), "prove_ms": round(c5["prove_split_ms"], 3)}
+                      "fri_ms": round(c5["fri_commit_split_ms"], 3) if c5.get("fri_commit_split_ms") else None,
+                      "prove_ms": round(c5["prove_split_ms"], 3) if c5.get("prove_split_ms") else None,
+                      "split_ok": c5.get("split_fri_and_proof_ok")}
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -501,31 +503,40 @@ def c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier):
         dr = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(dr, op=dist.ReduceOp.MAX)
         resident_per = float(dr.item()) / iters
-    # the FRI commit phase and a whole proof of the same blob, every layer split over the ranks (frieda_fri_split_*)
+    # the FRI commit phase and a whole proof of the same blob, every layer split over the ranks (frieda_fri_split_*).
+    # A widening row: its checks are REPORTED (split_fri_and_proof_ok), every rank agreeing on the
+    # outcome first, so that a failure here cannot take the C3 / C5 numbers of the line down with it.
     from frieda_b200.parallel import fri_commit_split, prove_split
     import frieda_b200 as F
     c5cfg = F.PcsConfig(2, 0, 64, 20)
-    roots, _ = fri_commit_split(ctx, blob, None, c5cfg)
-    assert roots[0].tobytes().hex() == C5_ROOT, "split FRI commit: layer-0 root != the oracle's commit root"
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        roots2, _ = fri_commit_split(ctx, blob, None, c5cfg)
-    torch.cuda.synchronize()
-    df = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    proot, proof = prove_split(ctx, blob, 1, c5cfg)
-    barrier()
-    t0 = time.perf_counter()
-    proot, proof = prove_split(ctx, blob, 1, c5cfg)
-    torch.cuda.synchronize()
-    dp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    fri_ms = prove_ms = None
+    split_ok, split_err = False, None
+    try:
+        roots, _ = fri_commit_split(ctx, blob, None, c5cfg)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            roots2, _ = fri_commit_split(ctx, blob, None, c5cfg)
+        torch.cuda.synchronize()
+        df = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        proot, proof = prove_split(ctx, blob, 1, c5cfg)
+        barrier()
+        t0 = time.perf_counter()
+        proot, proof = prove_split(ctx, blob, 1, c5cfg)
+        torch.cuda.synchronize()
+        dp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(df, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dp, op=dist.ReduceOp.MAX)
+        fri_ms, prove_ms = float(df.item()) / 3 * 1e3, float(dp.item()) * 1e3
+        split_ok = bool(roots[0].tobytes().hex() == C5_ROOT and np.array_equal(roots, roots2) and
+                        proot.hex() == C5_ROOT and F.verify_proof(proof, 1) and not F.verify_proof(proof, 2))
+    except Exception as e:  # noqa: BLE001 -- reported in the line
+        split_err = f"{type(e).__name__}: {e}"[:200]
     if distributed:
-        dist.all_reduce(df, op=dist.ReduceOp.MAX)
-        dist.all_reduce(dp, op=dist.ReduceOp.MAX)
-    fri_ms, prove_ms = float(df.item()) / 3 * 1e3, float(dp.item()) * 1e3
-    split_ok = (np.array_equal(roots, roots2) and proot.hex() == C5_ROOT and F.verify_proof(proof, 1)
-                and not F.verify_proof(proof, 2))
-    assert split_ok, "split FRI commit / proof of the 64 MiB blob failed its checks"
+        flag = torch.tensor([1 if split_ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        split_ok = bool(flag.item())
     exchange = ("single GPU" if world == 1 else
                 "NCCL all-gathers (peer mapping unavailable)" if _par._peer_memory_broken else
                 "peer-mapped memory: slices and roots read in place over NVLink by the library's kernels")
@@ -535,6 +546,7 @@ def c5_split(ctx, stream, torch, dist, distributed, rank, world, barrier):
             "root_matches_oracle": ok, "ms_per_blob": per * 1e3, "wall_ms_per_blob": wall_per * 1e3,
             "ms_per_blob_slices_resident": resident_per * 1e3 if resident_per else None,
             "fri_commit_split_ms": fri_ms, "prove_split_ms": prove_ms, "split_fri_and_proof_ok": split_ok,
+            "split_fri_error": split_err,
             "split_fri_note": "FriProver::commit / commit_and_generate_proof of the same blob (blowup 2^2, 64 queries, "
                               "pow 20) with every layer split over the ranks; host wall clock, max over ranks, H2D of the "
                               "blob included; layer-0 root == the oracle's commit root, proof verified by the host verifier",

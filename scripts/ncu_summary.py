@@ -11,8 +11,8 @@ import sys
 
 # ncu kernel name -> the name frieda_ctx_profile_read reports
 PROFILE_NAMES = [
-    ("merkle_bottom_kernel<0>", "merkle_bottom_cols"), ("merkle_bottom_kernel<1>", "fold_circle+merkle_bottom"),
-    ("merkle_bottom_kernel<2>", "fold_line+merkle_bottom"), ("merkle_bottom_kernel<3>", "merkle_mid"),
+    ("merkle_bottom_kernel<0", "merkle_bottom_cols"), ("merkle_bottom_kernel<1", "fold_circle+merkle_bottom"),
+    ("merkle_bottom_kernel<2", "fold_line+merkle_bottom"), ("merkle_bottom_kernel<3", "merkle_mid"),
     ("merkle_top_kernel", "merkle_top"), ("fri_tail_kernel", "fri_tail"), ("lde_warp_kernel", "lde"),
     ("lde_strided", "lde_strided"), ("fold_kernel", "fold"), ("pack_peers_kernel", "pack"), ("grind_kernel", "grind"),
 ]
