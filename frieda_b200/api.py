@@ -95,7 +95,7 @@ EXPORTS = [
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
     "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks",
-    "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_layer", "frieda_fri_split_combine",
+    "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_layer", "frieda_fri_split_combine", "frieda_fri_split_layers_peers",
     "frieda_fri_split_handoff", "frieda_fri_split_finish", "frieda_fri_split_decommit", "frieda_fri_split_assemble",
     "frieda_buffer_free", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
@@ -165,6 +165,7 @@ def load_library(build_if_missing: bool = True):
         "frieda_buffer_free": (None, [vp]),
         "frieda_fri_split_layer": (C.c_int, [vp, C.c_uint32, vp]),
         "frieda_fri_split_combine": (C.c_int, [vp, C.c_uint32, vp]),
+        "frieda_fri_split_layers_peers": (C.c_int, [vp, vp, vp, C.c_uint32]),
         "frieda_fri_split_handoff": (C.c_int, [vp, vp]),
         "frieda_fri_split_finish": (C.c_int, [vp, vp, vp, vp]),
         "frieda_decode_block": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint32, vp]),
@@ -542,6 +543,13 @@ class Context:
 
     def fri_split_combine(self, layer: int, subroots_dev_ptr: int):
         self._check(self._L.frieda_fri_split_combine(self._h, layer, subroots_dev_ptr))
+
+    def fri_split_layers_peers(self, peer_root_ptrs, peer_flag_ptrs, epoch: int):
+        """All split layers in one call; the subtree roots travel through peer-mapped memory (frieda_fri_split_layers_peers).
+        peer_root_ptrs[r] = base of rank r's symmetric roots area (64 x 32 bytes)."""
+        world = len(peer_root_ptrs)
+        mk = lambda ps: (C.c_void_p * world)(*[int(p) for p in ps])  # noqa: E731
+        self._check(self._L.frieda_fri_split_layers_peers(self._h, mk(peer_root_ptrs), mk(peer_flag_ptrs), epoch))
 
     def fri_split_handoff(self, cols_local_dev_ptr: int):
         """This rank's 4 x 2^handoff_log u32 share of the first unsplit layer -> the caller's device buffer."""

@@ -194,6 +194,7 @@ struct frieda_ctx {
     bool handed_off = false;
     bool keep = false;           // trees kept whole: a proof follows (frieda_fri_split_decommit)
     bool finished = false;       // FriProver::commit is complete, the state is still resident
+    bool peer_timeout_check = false;  // the layers ran over peer memory: `finish` reads the barrier-timeout flag
     frieda_pcs_config cfg{};
     size_t o_toptree = 0;        // keep: per split layer the top log2(world) levels (2 * world slots each)
     size_t o_best = 0, o_next = 0, o_queries = 0, o_nuniq = 0;
@@ -1571,13 +1572,10 @@ int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t
 
 // Layer `layer` of this rank's range: fold of the previous layer with its alpha (layers >= 1) fused into the leaf
 // hashing, rank-local subtree -> 32-byte subtree root (device memory, the all-gather's input).  Asynchronous.
-int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out) {
-  if (!ctx) return FRIEDA_ERR_ARG;
+// rank-local part of one split layer: this rank's columns (folded from the previous layer) and its subtree; the
+// subtree root goes to d_subroot_out (device; may be peer-visible memory)
+static int split_layer_local(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out) {
   frieda_ctx::SplitFri &sp = ctx->split;
-  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress (call frieda_fri_split_begin)");
-  if (!d_subroot_out) return ctx->fail_arg("null pointer");
-  if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
-  CU(cudaSetDevice(ctx->device));
   const Geom &g = sp.g;
   const uint32_t d = layer_log(g, layer) - sp.gl;  // log size of this rank's share
   MerkleBottomParams mp;
@@ -1602,10 +1600,37 @@ int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_o
   }
   mp.tree = at<uint8_t>(ctx, sp.o_tree[layer]);
   mp.tree_stride = sp.tree_slots[layer];
-  int rc = run_tree(ctx, src, mp, d, sp.levels_cfg[layer], sp.keep, 1, nullptr, 0, nullptr, nullptr, 0);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(d_subroot_out, mp.tree + 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  // the top kernel stores the subtree root straight into d_subroot_out: no copy-engine command sits between a
+  // layer's kernels and its barrier (on one GPU, copies of several virtual ranks share one engine queue, and a copy
+  // parked behind rank A's barrier would keep rank B from ever reaching it)
+  return run_tree(ctx, src, mp, d, sp.levels_cfg[layer], sp.keep, 1, d_subroot_out, 32, nullptr, nullptr, 0);
+}
+// top log2(world) levels over the `world` subtree roots already placed in slots [world, 2 world) of the layer's top
+// tree, then mix_root + draw alpha on this rank's copy of the channel
+static int split_layer_top(frieda_ctx *ctx, uint32_t layer, uint8_t *top) {
+  frieda_ctx::SplitFri &sp = ctx->split;
+  const Geom &g = sp.g;
+  KL("merkle_top", launch_merkle_top(ctx->stream, top, 2 * (size_t)sp.world, sp.gl, sp.keep ? 1 : 0,
+                                     at<uint8_t>(ctx, sp.o_roots) + 32 * (size_t)layer,
+                                     (size_t)g.n_layers * 32, at<Channel>(ctx, sp.o_chan), at<QM31>(ctx, sp.o_alpha) + layer,
+                                     g.n_layers, 1),
+     1);
   return FRIEDA_OK;
+}
+static uint8_t *split_top_tree(frieda_ctx *ctx, uint32_t layer) {
+  frieda_ctx::SplitFri &sp = ctx->split;
+  // heap order: the subtree roots are level gl; kept per layer when a proof follows (the decommitment's top levels)
+  return sp.keep ? at<uint8_t>(ctx, sp.o_toptree) + (size_t)layer * 2 * sp.world * 32 : at<uint8_t>(ctx, sp.o_top);
+}
+
+int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress (call frieda_fri_split_begin)");
+  if (!d_subroot_out) return ctx->fail_arg("null pointer");
+  if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
+  CU(cudaSetDevice(ctx->device));
+  return split_layer_local(ctx, layer, d_subroot_out);
 }
 
 // Top log2(world) levels over the gathered subtree roots (d_subroots = world * 32 bytes, rank order, device), then the
@@ -1617,16 +1642,51 @@ int frieda_fri_split_combine(frieda_ctx *ctx, uint32_t layer, const uint8_t *d_s
   if (!d_subroots) return ctx->fail_arg("null pointer");
   if (layer != sp.next_layer || layer >= sp.n_split) return ctx->fail_arg("split layers must be committed in order");
   CU(cudaSetDevice(ctx->device));
-  const Geom &g = sp.g;
-  // heap order: the subtree roots are level gl; kept per layer when a proof follows (the decommitment's top levels)
-  uint8_t *top = sp.keep ? at<uint8_t>(ctx, sp.o_toptree) + (size_t)layer * 2 * sp.world * 32 : at<uint8_t>(ctx, sp.o_top);
+  uint8_t *top = split_top_tree(ctx, layer);
   CU(cudaMemcpyAsync(top + (size_t)sp.world * 32, d_subroots, (size_t)sp.world * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-  KL("merkle_top", launch_merkle_top(ctx->stream, top, 2 * (size_t)sp.world, sp.gl, sp.keep ? 1 : 0,
-                                     at<uint8_t>(ctx, sp.o_roots) + 32 * (size_t)layer,
-                                     (size_t)g.n_layers * 32, at<Channel>(ctx, sp.o_chan), at<QM31>(ctx, sp.o_alpha) + layer,
-                                     g.n_layers, 1),
-     1);
+  int rc = split_layer_top(ctx, layer, top);
+  if (rc) return rc;
   sp.next_layer = layer + 1;
+  return FRIEDA_OK;
+}
+
+// All split layers in ONE call per rank, the per-layer exchange done by the library's own kernels over peer-mapped
+// memory (NVLink / NVSwitch) instead of a host-driven all-gather per layer: layer l's subtree root is stored into
+// slot l of this rank's symmetric roots area (peer_roots[rank], >= 64 slots of 32 bytes), a stream-ordered barrier
+// kernel (flag channel 6, epoch * 64 + l) makes it visible, gather_roots_kernel reads the `world` roots where they
+// lie, and every rank hashes the top levels and runs the layer's transcript step.  A final barrier keeps a rank from
+// overwriting slot l in its next call while a peer still reads this call's.  Asynchronous; a peer that never arrives
+// (~20 s) is reported by frieda_fri_split_finish.  epoch: the caller's call counter over these flag arrays, as in
+// frieda_commit_split_peers.
+int frieda_fri_split_layers_peers(frieda_ctx *ctx, uint8_t *const *peer_roots, uint32_t *const *peer_flags,
+                                  uint32_t epoch) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  frieda_ctx::SplitFri &sp = ctx->split;
+  if (!sp.active || sp.handed_off) return ctx->fail_arg("no split FRI commit in progress (call frieda_fri_split_begin)");
+  if (!peer_roots || !peer_flags) return ctx->fail_arg("null pointer");
+  if (sp.next_layer != 0) return ctx->fail_arg("split layers were already committed one by one");
+  if (sp.world > MAX_PEERS || sp.n_split > 62) return ctx->fail_arg("too many ranks or split layers for the peer form");
+  CU(cudaSetDevice(ctx->device));
+  PeerFlags fl;
+  for (uint32_t r = 0; r < MAX_PEERS; r++) {
+    fl.p[r] = r < sp.world ? peer_flags[r] : nullptr;
+    if (r < sp.world && (!fl.p[r] || !peer_roots[r])) return ctx->fail_arg("null peer pointer");
+  }
+  int *d_timeout = reinterpret_cast<int *>(ctx->d_scratch + 4096);
+  CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
+  sp.peer_timeout_check = true;
+  for (uint32_t layer = 0; layer < sp.n_split; layer++) {
+    int rc = split_layer_local(ctx, layer, peer_roots[sp.rank] + 32 * (size_t)layer);
+    if (rc) return rc;
+    KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, sp.world, sp.rank, 6, epoch * 64u + layer, d_timeout), 1);
+    PeerPtrs rt;
+    for (uint32_t r = 0; r < MAX_PEERS; r++) rt.p[r] = r < sp.world ? peer_roots[r] + 32 * (size_t)layer : nullptr;
+    uint8_t *top = split_top_tree(ctx, layer);
+    KL("gather_roots", launch_gather_roots(ctx->stream, rt, sp.world, top), 1);
+    if ((rc = split_layer_top(ctx, layer, top))) return rc;
+    sp.next_layer = layer + 1;
+  }
+  KL("peer_barrier", launch_peer_barrier(ctx->stream, fl, sp.world, sp.rank, 6, epoch * 64u + 63u, d_timeout), 1);
   return FRIEDA_OK;
 }
 
@@ -1714,13 +1774,20 @@ int frieda_fri_split_finish(frieda_ctx *ctx, const uint32_t *d_cols_all, uint8_t
   tp.error_flag = at<int>(ctx, w.o_err);
   tp.tt = table(ctx);
   KL("fri_tail", launch_tail(ctx->stream, tp, 1), 1);
-  int err_flag = 0;
+  int err_flag = 0, timed_out = 0;
+  if (sp.peer_timeout_check)
+    CU(cudaMemcpyAsync(&timed_out, ctx->d_scratch + 4096, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(layer_roots_out, roots, (size_t)g.n_layers * 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(last_poly_out, at<QM31>(ctx, w.o_last), sizeof(QM31) << g.log_last, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(&err_flag, at<int>(ctx, w.o_err), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   sp.finished = true;
   if (!sp.keep) sp.active = false;
+  if (timed_out) {
+    sp.active = false;
+    ctx->err = "peer barrier timed out: a rank of the split FRI commit did not arrive";
+    return FRIEDA_ERR_CUDA;
+  }
   if (err_flag) {
     sp.active = false;
     return ctx->fail_arg("reference panics: invalid degree", FRIEDA_ERR_PANIC);

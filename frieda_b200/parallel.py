@@ -69,6 +69,9 @@ class _PeerState:
         self.flags = symm_mem.empty(512, dtype=torch.int32, device=dev)
         self.flags.zero_()
         self.h_flags = symm_mem.rendezvous(self.flags, group=g)
+        # per-layer subtree roots of a split FRI commit (frieda_fri_split_layers_peers): slot l of rank r's area
+        self.fri_roots = symm_mem.empty(64 * 32, dtype=torch.uint8, device=dev)
+        self.h_fri_roots = symm_mem.rendezvous(self.fri_roots, group=g)
         self.h_flags.barrier(channel=0)
         torch.cuda.current_stream(dev).synchronize()
         self.epoch = 0
@@ -76,6 +79,7 @@ class _PeerState:
         self.slice_ptrs = [int(p) for p in self.h_in.buffer_ptrs]
         self.root_ptrs = [int(p) + 32 * r for r, p in enumerate(self.h_roots.buffer_ptrs)]
         self.flag_ptrs = [int(p) for p in self.h_flags.buffer_ptrs]
+        self.fri_root_ptrs = [int(p) for p in self.h_fri_roots.buffer_ptrs]
 
 
 _peer_states = {}
@@ -125,7 +129,7 @@ def commit_split_peers(ctx, host, n_bytes: int, log_blowup_factor: int, rank: in
 
 
 def prove_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,
-                all_gather=None, all_gather_bytes=None):
+                all_gather=None, all_gather_bytes=None, peer_memory: Optional[bool] = None):
     """commit_and_generate_proof (src/proof.rs:32-77) of ONE blob split across the ranks of `group`: the split FRI commit
     with every tree kept, then on every rank proof of work + queries (replicated) and the rank's share of the
     decommitment; the shares are all-gathered (a few hundred KB) and merged on every rank.  Returns (root, Proof),
@@ -137,7 +141,8 @@ def prove_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, wo
     distributed = dist.is_available() and dist.is_initialized()
     if world is None:
         world = dist.get_world_size(group) if distributed else 1
-    roots, _ = fri_commit_split(ctx, data, seed, cfg, group, rank, world, all_gather, keep_trees=True)
+    roots, _ = fri_commit_split(ctx, data, seed, cfg, group, rank, world, all_gather, keep_trees=True,
+                                peer_memory=peer_memory)
     share = ctx.fri_split_decommit()
     if all_gather_bytes is None:
         def all_gather_bytes(b):
@@ -150,7 +155,7 @@ def prove_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, wo
 
 
 def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, world: Optional[int] = None,
-                     all_gather=None, keep_trees: bool = False):
+                     all_gather=None, keep_trees: bool = False, peer_memory: Optional[bool] = None):
     """FriProver::commit (src/proof.rs:52-57) of ONE blob with every layer split across the ranks of `group`
     (frieda_fri_split_*): per split layer a rank-local fused fold + subtree, an all-gather of `world` 32-byte
     subtree roots (NCCL over NVLink), the top levels and the channel step on every rank; then an all-gather of the
@@ -159,9 +164,15 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
     Context.fri_commit_batch on one GPU.
 
     all_gather(tensor) -> tensor of shape (world, *tensor.shape): the transport; default torch.distributed over
-    `group` (tests with several contexts on one GPU pass their own)."""
+    `group` (tests with several contexts on one GPU pass their own).
+
+    peer_memory (default: tried first on real ranks): the split layers run as ONE library call per rank
+    (frieda_fri_split_layers_peers) whose per-layer exchange of subtree roots is done by the library's kernels over
+    peer-mapped symmetric memory -- no host-driven collective per layer; otherwise one NCCL all-gather of `world`
+    roots per layer."""
     import torch
     import torch.distributed as dist
+    global _peer_memory_broken
     distributed = dist.is_available() and dist.is_initialized()
     if world is None:
         world = dist.get_world_size(group) if distributed else 1
@@ -174,6 +185,7 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
     dev = torch.device("cuda", ctx.device) if on_gpu else torch.device("cpu")
     # the collectives are ordered on the context's stream, like its kernels
     scope = torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)) if on_gpu else contextlib.nullcontext()
+    real_ranks = on_gpu and world > 1 and distributed and all_gather is None
     if all_gather is None:
         def all_gather(t):
             if world == 1:
@@ -181,8 +193,19 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
             return out
+    st = None
+    if real_ranks and peer_memory is not False and (peer_memory or not _peer_memory_broken):
+        try:
+            st = _peer_state(ctx, group, 1 << 20)
+        except (ImportError, RuntimeError, AttributeError) as e:
+            # collective: fails on every rank alike, so all of them take the NCCL form below
+            if peer_memory:
+                raise
+            _peer_memory_broken = True
+            import warnings
+            warnings.warn(f"peer-mapped split FRI commit unavailable ({e}); using NCCL all-gathers")
     full = None
-    if on_gpu and world > 1 and distributed and all_gather is None:
+    if real_ranks:
         # every rank needs the whole blob: each uploads 1/world of it over its own PCIe link, NCCL all-gathers the
         # slices over NVLink (as commit_split's NCCL form does), and the library starts from device memory
         import numpy as np
@@ -203,11 +226,15 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
         n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
     with scope:
         # (allocated inside the scope: every tensor the library writes is touched on the context's stream only)
-        sub = torch.empty(32, dtype=torch.uint8, device=dev)
-        for layer in range(n_split):
-            ctx.fri_split_layer(layer, sub.data_ptr())
-            roots = all_gather(sub)
-            ctx.fri_split_combine(layer, roots.data_ptr())
+        if st is not None:
+            st.epoch += 1
+            ctx.fri_split_layers_peers(st.fri_root_ptrs, st.flag_ptrs, st.epoch)
+        else:
+            sub = torch.empty(32, dtype=torch.uint8, device=dev)
+            for layer in range(n_split):
+                ctx.fri_split_layer(layer, sub.data_ptr())
+                roots = all_gather(sub)
+                ctx.fri_split_combine(layer, roots.data_ptr())
         mine = torch.empty(4 << handoff_log, dtype=torch.int32, device=dev)
         ctx.fri_split_handoff(mine.data_ptr())
         cols_all = all_gather(mine)

@@ -244,6 +244,14 @@ int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t
 int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out);
 /* d_subroots: world * 32 bytes, rank order, device.  Top levels, root of the layer, mix_root, draw alpha. */
 int frieda_fri_split_combine(frieda_ctx *ctx, uint32_t layer, const uint8_t *d_subroots);
+/* ALL split layers in one call, the per-layer exchange of subtree roots done by the library's own kernels over
+ * peer-mapped memory (NVLink / NVSwitch) -- replaces the per-layer {frieda_fri_split_layer, all-gather,
+ * frieda_fri_split_combine} sequence.  peer_roots[r]: base of rank r's symmetric roots area (>= 64 slots of 32 bytes,
+ * mapped on this GPU); peer_flags[r]: rank r's flag array as in frieda_commit_split_peers (channel 6 is used);
+ * epoch: the caller's call counter over these flag arrays (same value on every rank, increasing).  Asynchronous; a
+ * peer that never arrives is reported by frieda_fri_split_finish (FRIEDA_ERR_CUDA after ~20 s). */
+int frieda_fri_split_layers_peers(frieda_ctx *ctx, uint8_t *const *peer_roots, uint32_t *const *peer_flags,
+                                  uint32_t epoch);
 /* Folds the last split layer into this rank's share of the next one, written to d_cols_local_out: 4 columns x
  * 2^handoff_log u32 of the caller's device memory (handoff_log from `begin`) -- the input of the all-gather of columns. */
 int frieda_fri_split_handoff(frieda_ctx *ctx, uint32_t *d_cols_local_out);

@@ -3,6 +3,7 @@ bit-exact, on every intermediate (coefficients, twiddles, evaluations, every Mer
 FRI layer, alphas, nonce, queries, witnesses), plus the reference's own test behaviours
 (src/commit.rs:28-38, src/proof.rs:119-193, src/lib.rs:52-85) through the product API."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -12,6 +13,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 P = (1 << 31) - 1
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def pattern(n):
@@ -777,6 +779,67 @@ def test_fri_commit_split_virtual_ranks(torch_mod, blob_bytes, kind, n_bytes, se
         finally:
             for c in ctxs:
                 c.close()
+
+
+PEER_LAYERS_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+import frieda_b200 as F
+from frieda_b200 import api
+from oracle import oracle as O
+# `world` contexts on ONE GPU play the ranks; plain device buffers stand in for the peer-mapped roots areas and flag
+# arrays.  Every rank's whole layer loop is enqueued (asynchronously) before anyone synchronises, and the ranks'
+# barrier kernels then meet on the GPU.
+for n_bytes, cfg, seed, worlds in ((131072, (4, 0, 20, 12), 3, (2, 4)), (1 << 20, (2, 1, 20, 10), None, (4,)),
+                                   (40000, (3, 1, 17, 10), 5, (2,))):
+    data = O.splitmix64_bytes(0x4652494544414236 + n_bytes, n_bytes)
+    oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
+    oroot, oproof = O.prove(data, seed, O.make_config(*cfg))
+    pcs = F.PcsConfig(*cfg)
+    for world in worlds:
+        ctxs = [F.Context(0) for _ in range(world)]
+        areas = torch.zeros((world, 64 * 32), dtype=torch.uint8, device="cuda")
+        flags = torch.zeros((world, 512), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        root_ptrs = [areas[r].data_ptr() for r in range(world)]
+        flag_ptrs = [flags[r].data_ptr() for r in range(world)]
+        for epoch, keep in ((1, False), (2, False), (3, True)):  # the slots are reused under an advancing epoch
+            shapes = [c.fri_split_begin(data, seed, pcs, r, world, keep_trees=keep) for r, c in enumerate(ctxs)]
+            n_split, n_layers, handoff_log = shapes[0]
+            for c in ctxs:
+                c.fri_split_layers_peers(root_ptrs, flag_ptrs, epoch)
+            cols = torch.zeros((world, 4 << handoff_log), dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            for r, c in enumerate(ctxs):
+                c.fri_split_handoff(cols[r].data_ptr())
+            torch.cuda.synchronize()
+            for r, c in enumerate(ctxs):
+                roots, last = c.fri_split_finish(cols.data_ptr(), n_layers, cfg[1])
+                assert [x.tobytes() for x in roots] == oroots, (n_bytes, world, r, epoch)
+                assert [tuple(int(x) for x in q) for q in last] == olast, (n_bytes, world, r, epoch)
+            if keep:
+                proof = api.split_assemble([c.fri_split_decommit() for c in ctxs])
+                assert proof.serialize() == oproof.serialize(), (n_bytes, world)
+        for c in ctxs:
+            c.close()
+print("PEER_LAYERS_OK")
+"""
+
+
+def test_fri_split_layers_peers_virtual_ranks(tmp_path):
+    # frieda_fri_split_layers_peers on ONE GPU: separate process so that CUDA_DEVICE_MAX_CONNECTIONS can give every
+    # virtual rank's stream its own hardware queue (ranks that shared one would wait on each other's barrier kernels)
+    import subprocess
+    import sys
+    script = tmp_path / "peer_layers_worker.py"
+    script.write_text(PEER_LAYERS_WORKER % {"root": ROOT})
+    # ... and CUDA_MODULE_LOADING=EAGER: with lazy loading the FIRST launch of a kernel may synchronise the device,
+    # which would block the host behind rank 0's spinning barrier before rank 1 is even enqueued (real ranks are
+    # separate processes and only serialise on that first load)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PEER_LAYERS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def split_prove_virtual(torch, data, seed, cfg, world):

@@ -29,20 +29,25 @@ for n_bytes, blow in ((100003, 2), (1 << 20, 2), (131072, 4), (3000, 3), (8 << 2
             want = O.commit(data.tobytes(), blow)
             assert parallel.commit_split(ctx, data, blow, peer_memory=peers) == want, (n_bytes, blow, peers, k)
 assert not parallel._peer_memory_broken
-# FRI commit phase of one blob with every layer split over the two ranks (NCCL all-gathers of the subtree roots)
+# FRI commit phase of one blob with every layer split over the two ranks: the per-layer exchange of subtree roots as
+# NCCL all-gathers (peers False) and inside the library over peer-mapped memory (peers True: one call for all layers;
+# run twice so that the root slots are reused under an advanced epoch)
 for n_bytes, cfg, seed in ((1 << 20, (2, 0, 20, 12), 7), (131072, (4, 0, 20, 20), None), (8 << 20, (2, 1, 20, 12), 3)):
     data = O.splitmix64_bytes(0x4652494544414236 + n_bytes, n_bytes)
-    roots, last = parallel.fri_commit_split(ctx, data, seed, F.PcsConfig(*cfg))
     oroots, olast = O.fri_commit(data, seed, O.make_config(*cfg))
-    assert [r.tobytes() for r in roots] == oroots, (n_bytes, cfg)
-    assert [tuple(int(x) for x in q) for q in last] == olast, (n_bytes, cfg)
+    for peers in (False, True, True):
+        roots, last = parallel.fri_commit_split(ctx, data, seed, F.PcsConfig(*cfg), peer_memory=peers)
+        assert [r.tobytes() for r in roots] == oroots, (n_bytes, cfg, peers)
+        assert [tuple(int(x) for x in q) for q in last] == olast, (n_bytes, cfg, peers)
 # ... and the whole proof: replicated grind + queries, owner-serves-path decommitment, shares all-gathered and merged
 for n_bytes, cfg, seed in ((1 << 20, (2, 0, 20, 12), 7), (131072, (4, 0, 64, 16), 5)):
     data = O.splitmix64_bytes(0x4652494544414236 + n_bytes, n_bytes)
-    root, proof = parallel.prove_split(ctx, data, seed, F.PcsConfig(*cfg))
     oroot, opr = O.prove(data, seed, O.make_config(*cfg))
-    assert root == oroot and proof.serialize() == opr.serialize(), (n_bytes, cfg)
-    assert F.verify_proof(proof, seed)
+    for peers in (False, True):
+        root, proof = parallel.prove_split(ctx, data, seed, F.PcsConfig(*cfg), peer_memory=peers)
+        assert root == oroot and proof.serialize() == opr.serialize(), (n_bytes, cfg, peers)
+        assert F.verify_proof(proof, seed)
+assert not parallel._peer_memory_broken
 ctx.close()
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTI_GPU_OK")
