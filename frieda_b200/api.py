@@ -95,7 +95,7 @@ EXPORTS = [
     "frieda_commit_split_local_device", "frieda_commit_split_local_peers", "frieda_merkle_combine_peers",
     "frieda_commit_split_peers",
     "frieda_merkle_combine", "frieda_decode_block", "frieda_decode_blocks",
-    "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_layer", "frieda_fri_split_combine", "frieda_fri_split_layers_peers",
+    "frieda_fri_split_begin", "frieda_fri_split_begin_device", "frieda_fri_split_begin_peers", "frieda_fri_split_layer", "frieda_fri_split_combine", "frieda_fri_split_layers_peers",
     "frieda_fri_split_handoff", "frieda_fri_split_finish", "frieda_fri_split_decommit", "frieda_fri_split_assemble",
     "frieda_buffer_free", "frieda_pass_pack", "frieda_pass_lde", "frieda_pass_merkle", "frieda_pass_fold",
     "frieda_twiddles", "frieda_debug_fetch", "frieda_ctx_set_debug_keep",
@@ -165,6 +165,8 @@ def load_library(build_if_missing: bool = True):
         "frieda_buffer_free": (None, [vp]),
         "frieda_fri_split_layer": (C.c_int, [vp, C.c_uint32, vp]),
         "frieda_fri_split_combine": (C.c_int, [vp, C.c_uint32, vp]),
+        "frieda_fri_split_begin_peers": (C.c_int, [vp, vp, C.c_size_t, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp,
+                                                   C.c_size_t, vp, C.c_uint32, vp, vp, vp]),
         "frieda_fri_split_layers_peers": (C.c_int, [vp, vp, vp, C.c_uint32]),
         "frieda_fri_split_handoff": (C.c_int, [vp, vp]),
         "frieda_fri_split_finish": (C.c_int, [vp, vp, vp, vp]),
@@ -536,6 +538,19 @@ class Context:
             rc = self._L.frieda_fri_split_begin(self._h, a.ctypes.data, a.size, sp, C.byref(cfg), rank, world,
                                                 int(keep_trees), C.byref(ns), C.byref(nl), C.byref(hl))
         self._check(rc)
+        return int(ns.value), int(nl.value), int(hl.value)
+
+    def fri_split_begin_peers(self, data, seed: Optional[int], cfg: PcsConfig, rank: int, peer_slice_ptrs, slice_len: int,
+                              peer_flag_ptrs, epoch: int, keep_trees: bool = False) -> Tuple[int, int, int]:
+        """fri_split_begin with the blob in peer-mapped slices: this rank uploads only slice `rank` of `data`."""
+        world = len(peer_slice_ptrs)
+        mk = lambda ps: (C.c_void_p * world)(*[int(p) for p in ps])  # noqa: E731
+        ns, nl, hl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        sp = C.byref(C.c_uint64(seed)) if seed is not None else None
+        a = _as_u8(data)
+        self._check(self._L.frieda_fri_split_begin_peers(self._h, a.ctypes.data, a.size, sp, C.byref(cfg), rank, world,
+                                                         int(keep_trees), mk(peer_slice_ptrs), slice_len,
+                                                         mk(peer_flag_ptrs), epoch, C.byref(ns), C.byref(nl), C.byref(hl)))
         return int(ns.value), int(nl.value), int(hl.value)
 
     def fri_split_layer(self, layer: int, subroot_dev_ptr: int):

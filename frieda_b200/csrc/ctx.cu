@@ -1465,12 +1465,21 @@ void split_layout_remainder(const frieda_ctx::SplitFri &sp, Plan &w, size_t *end
   if (end_out) *end_out = fb.off + 4096;
 }
 
+// peers != nullptr: the blob lies in `world` slices of slice_len bytes behind peer-mapped pointers; this rank uploads
+// its own slice (data = the whole blob in host memory, or nullptr when the slices are already resident), a barrier
+// kernel (flag channel 7) orders the uploads, and the packing kernel reads every slice in place over NVLink
+struct SplitPeerInput {
+  PeerPtrs slices;
+  PeerFlags flags;
+  size_t slice_len;
+  uint32_t epoch;
+};
 int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool device_input, const uint64_t *seed_or_null,
                      const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees, uint32_t *n_split_out,
-                     uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+                     uint32_t *n_layers_out, uint32_t *handoff_log_out, const SplitPeerInput *peers = nullptr) {
   if (!ctx) return FRIEDA_ERR_ARG;
   ctx->split.active = false;
-  if ((!data && len) || !cfg) return ctx->fail_arg("null pointer");
+  if ((!data && len && !peers) || !cfg) return ctx->fail_arg("null pointer");
   if (world == 0 || (world & (world - 1)) || world > MAX_PEERS || rank >= world)
     return ctx->fail_arg("world must be a power of two <= 64 and > rank");
   CU(cudaSetDevice(ctx->device));
@@ -1526,18 +1535,9 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   }
   if ((rc = ensure_arena(ctx, bp.off))) return rc;
   ctx->have_last = false;
-  const uint8_t *d_in = data;
-  if (!device_input) {
-    uint8_t *stage = at<uint8_t>(ctx, o_in);
-    if (len) CU(cudaMemcpyAsync(stage, data, len, cudaMemcpyHostToDevice, ctx->stream));
-    d_in = stage;
-  }
-  uint32_t *coef = at<uint32_t>(ctx, sp.o_coef);
-  KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
-  LdeRange rg{(size_t)rank << rlog, rlog};
-  KL("lde", launch_lde(ctx->stream, coef, at<uint32_t>(ctx, sp.o_cols[0]), g.p, g.beta, 1, g.n_felts, table(ctx),
-                       half_initial_point(g), &rg),
-     (g.p > 15 ? 2 : 1));
+  // (the small copies and memsets first: nothing that needs a copy engine may follow the peer barrier below in
+  // stream order -- on one GPU the engine queue is shared by the virtual ranks of the tests, and a copy parked behind
+  // rank A's barrier would keep rank B's upload from ever starting)
   const uint64_t *d_seed = nullptr;
   if (seed_or_null) {
     CU(cudaMemcpyAsync(at<uint64_t>(ctx, sp.o_seed), seed_or_null, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1545,6 +1545,30 @@ int split_begin_impl(frieda_ctx *ctx, const uint8_t *data, size_t len, bool devi
   }
   KL("channel_init", launch_channel_init(ctx->stream, at<Channel>(ctx, sp.o_chan), d_seed, 1), 1);
   CU(cudaMemsetAsync(at<int>(ctx, sp.o_err), 0, sizeof(int), ctx->stream));
+  const uint8_t *d_in = data;
+  uint32_t *coef = at<uint32_t>(ctx, sp.o_coef);
+  if (peers) {
+    const size_t lo = std::min(len, (size_t)rank * peers->slice_len), hi = std::min(len, lo + peers->slice_len);
+    if (data && hi > lo)
+      CU(cudaMemcpyAsync(const_cast<uint8_t *>(peers->slices.p[rank]), data + lo, hi - lo, cudaMemcpyHostToDevice,
+                         ctx->stream));
+    int *d_timeout = reinterpret_cast<int *>(ctx->d_scratch + 4096);
+    CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
+    sp.peer_timeout_check = true;
+    KL("peer_barrier", launch_peer_barrier(ctx->stream, peers->flags, world, rank, 7, peers->epoch, d_timeout), 1);
+    KL("pack", launch_pack_peers(ctx->stream, peers->slices, world, rank, peers->slice_len, len, g.n_felts, g.p, coef), 1);
+  } else {
+    if (!device_input) {
+      uint8_t *stage = at<uint8_t>(ctx, o_in);
+      if (len) CU(cudaMemcpyAsync(stage, data, len, cudaMemcpyHostToDevice, ctx->stream));
+      d_in = stage;
+    }
+    KL("pack", launch_pack(ctx->stream, d_in, len, align_up(len ? len : 1, 16), 1, g.n_felts, g.p, coef), 1);
+  }
+  LdeRange rg{(size_t)rank << rlog, rlog};
+  KL("lde", launch_lde(ctx->stream, coef, at<uint32_t>(ctx, sp.o_cols[0]), g.p, g.beta, 1, g.n_felts, table(ctx),
+                       half_initial_point(g), &rg),
+     (g.p > 15 ? 2 : 1));
   sp.next_layer = 0;
   sp.handed_off = false;
   sp.finished = false;
@@ -1568,6 +1592,29 @@ int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t
                                   uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out) {
   return split_begin_impl(ctx, d_data, len, true, seed_or_null, cfg, rank, world, keep_trees, n_split_layers_out,
                           n_layers_out, handoff_log_out);
+}
+
+// The blob in peer-mapped slices (as frieda_commit_split_peers): this rank uploads slice `rank` of `data` over its own
+// PCIe link, and the packing kernel reads all slices where they lie (the input all-gather is its loads over NVLink).
+int frieda_fri_split_begin_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                                 const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
+                                 uint8_t *const *peer_slices, size_t slice_len, uint32_t *const *peer_flags, uint32_t epoch,
+                                 uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out) {
+  if (!ctx) return FRIEDA_ERR_ARG;
+  if (!peer_slices || !peer_flags) return ctx->fail_arg("null pointer");
+  if (world == 0 || world > MAX_PEERS || rank >= world) return ctx->fail_arg("world must be a power of two <= 64 and > rank");
+  if (slice_len == 0 || (slice_len & 15) || (uint64_t)slice_len * world < len)
+    return ctx->fail_arg("slice_len must be a multiple of 16 with world * slice_len >= len");
+  SplitPeerInput pi;
+  for (uint32_t r = 0; r < MAX_PEERS; r++) {
+    pi.slices.p[r] = r < world ? peer_slices[r] : nullptr;
+    pi.flags.p[r] = r < world ? peer_flags[r] : nullptr;
+    if (r < world && (!pi.slices.p[r] || !pi.flags.p[r])) return ctx->fail_arg("null peer pointer");
+  }
+  pi.slice_len = slice_len;
+  pi.epoch = epoch;
+  return split_begin_impl(ctx, data, len, false, seed_or_null, cfg, rank, world, keep_trees, n_split_layers_out,
+                          n_layers_out, handoff_log_out, &pi);
 }
 
 // Layer `layer` of this rank's range: fold of the previous layer with its alpha (layers >= 1) fused into the leaf
@@ -1673,7 +1720,7 @@ int frieda_fri_split_layers_peers(frieda_ctx *ctx, uint8_t *const *peer_roots, u
     if (r < sp.world && (!fl.p[r] || !peer_roots[r])) return ctx->fail_arg("null peer pointer");
   }
   int *d_timeout = reinterpret_cast<int *>(ctx->d_scratch + 4096);
-  CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));
+  if (!sp.peer_timeout_check) CU(cudaMemsetAsync(d_timeout, 0, sizeof(int), ctx->stream));  // (begin_peers cleared it)
   sp.peer_timeout_check = true;
   for (uint32_t layer = 0; layer < sp.n_split; layer++) {
     int rc = split_layer_local(ctx, layer, peer_roots[sp.rank] + 32 * (size_t)layer);

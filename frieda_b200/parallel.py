@@ -148,9 +148,25 @@ def prove_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = None, wo
         def all_gather_bytes(b):
             if world == 1:
                 return [b]
-            out = [None] * world
-            dist.all_gather_object(out, b, group=group)
-            return out
+            if not getattr(ctx, "is_cuda", True):
+                out = [None] * world
+                dist.all_gather_object(out, b, group=group)
+                return out
+            # two tensor collectives (lengths, then the shares padded to the longest) instead of all_gather_object's
+            # pickling round trips: the shares are a few hundred KB
+            import numpy as np
+            import torch
+            dev = torch.device("cuda", ctx.device)
+            lens = torch.zeros(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(lens, torch.tensor([len(b)], dtype=torch.int64, device=dev), group=group)
+            lens = [int(x) for x in lens.cpu()]
+            cap = (max(lens) + 15) // 16 * 16
+            mine = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            mine[: len(b)].copy_(torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()))
+            allb = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine, group=group)
+            host = allb.cpu().numpy()
+            return [host[r * cap: r * cap + lens[r]].tobytes() for r in range(world)]
     return roots[0].tobytes(), split_assemble(all_gather_bytes(share))
 
 
@@ -194,9 +210,15 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             dist.all_gather_into_tensor(out, t.reshape((1,) + tuple(t.shape)).contiguous(), group=group)
             return out
     st = None
+    host = per = None
+    if real_ranks:
+        import numpy as np
+        host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        host = host.reshape(-1).view(np.uint8)
+        per = slice_bounds(host.size, 0, world)[1]
     if real_ranks and peer_memory is not False and (peer_memory or not _peer_memory_broken):
         try:
-            st = _peer_state(ctx, group, 1 << 20)
+            st = _peer_state(ctx, group, max(per, 1 << 20))
         except (ImportError, RuntimeError, AttributeError) as e:
             # collective: fails on every rank alike, so all of them take the NCCL form below
             if peer_memory:
@@ -205,29 +227,31 @@ def fri_commit_split(ctx, data, seed, cfg, group=None, rank: Optional[int] = Non
             import warnings
             warnings.warn(f"peer-mapped split FRI commit unavailable ({e}); using NCCL all-gathers")
     full = None
-    if real_ranks:
+    shape = None
+    if st is not None:
+        # the blob travels like commit_split_peers' input: each rank uploads its slice into the symmetric buffer and
+        # the packing kernel reads all slices where they lie
+        st.epoch += 1
+        shape = ctx.fri_split_begin_peers(host, seed, cfg, rank, st.slice_ptrs, per, st.flag_ptrs, st.epoch,
+                                          keep_trees=keep_trees)
+    elif real_ranks and per >= (1 << 16):
         # every rank needs the whole blob: each uploads 1/world of it over its own PCIe link, NCCL all-gathers the
         # slices over NVLink (as commit_split's NCCL form does), and the library starts from device memory
-        import numpy as np
-        host = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
-        host = host.reshape(-1).view(np.uint8)
-        per = slice_bounds(host.size, 0, world)[1]
-        if per >= (1 << 16):
-            with scope:
-                full = torch.empty(per * world, dtype=torch.uint8, device=dev)
-                lo, hi = slice_bounds(host.size, rank, world)
-                mine = torch.zeros(per, dtype=torch.uint8, device=dev)
-                if hi > lo:
-                    mine[: hi - lo].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
-                dist.all_gather_into_tensor(full, mine, group=group)
-            n_split, n_layers, handoff_log = ctx.fri_split_begin(None, seed, cfg, rank, world, device_ptr=full.data_ptr(),
-                                                                 length=host.size, keep_trees=keep_trees)
-    if full is None:
-        n_split, n_layers, handoff_log = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
+        with scope:
+            full = torch.empty(per * world, dtype=torch.uint8, device=dev)
+            lo, hi = slice_bounds(host.size, rank, world)
+            mine = torch.zeros(per, dtype=torch.uint8, device=dev)
+            if hi > lo:
+                mine[: hi - lo].copy_(torch.from_numpy(host[lo:hi]), non_blocking=True)
+            dist.all_gather_into_tensor(full, mine, group=group)
+        shape = ctx.fri_split_begin(None, seed, cfg, rank, world, device_ptr=full.data_ptr(), length=host.size,
+                                    keep_trees=keep_trees)
+    if shape is None:
+        shape = ctx.fri_split_begin(data, seed, cfg, rank, world, keep_trees=keep_trees)
+    n_split, n_layers, handoff_log = shape
     with scope:
         # (allocated inside the scope: every tensor the library writes is touched on the context's stream only)
         if st is not None:
-            st.epoch += 1
             ctx.fri_split_layers_peers(st.fri_root_ptrs, st.flag_ptrs, st.epoch)
         else:
             sub = torch.empty(32, dtype=torch.uint8, device=dev)

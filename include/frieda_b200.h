@@ -239,6 +239,14 @@ int frieda_fri_split_begin(frieda_ctx *ctx, const uint8_t *data, size_t len, con
 int frieda_fri_split_begin_device(frieda_ctx *ctx, const uint8_t *d_data, size_t len, const uint64_t *seed_or_null,
                                   const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
                                   uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out);
+/* Same with the blob in `world` peer-mapped slices of slice_len bytes (a multiple of 16; the symmetric buffers of
+ * frieda_commit_split_peers): this rank uploads slice `rank` of `data` (the whole blob in host memory; NULL = the slices
+ * are already resident) over its own PCIe link, a barrier kernel (flag channel 7, `epoch`) orders the uploads, and the
+ * packing kernel reads every slice in place over NVLink.  Asynchronous. */
+int frieda_fri_split_begin_peers(frieda_ctx *ctx, const uint8_t *data, size_t len, const uint64_t *seed_or_null,
+                                 const frieda_pcs_config *cfg, uint32_t rank, uint32_t world, int keep_trees,
+                                 uint8_t *const *peer_slices, size_t slice_len, uint32_t *const *peer_flags, uint32_t epoch,
+                                 uint32_t *n_split_layers_out, uint32_t *n_layers_out, uint32_t *handoff_log_out);
 /* Layer `layer` on this rank's range (fold of the previous layer fused into the leaf hashing) -> its subtree root,
  * 32 bytes of device memory (the all-gather's input). */
 int frieda_fri_split_layer(frieda_ctx *ctx, uint32_t layer, uint8_t *d_subroot_out);
