@@ -858,6 +858,10 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     if (f == W_CUDA) return ctx->fail_arg("proof readback failed on the copy stream", FRIEDA_ERR_CUDA);
     return ctx->fail_arg("out of host memory", FRIEDA_ERR_ALLOC);
   };
+  // the waves as a function of their own: whichever way it leaves, the epilogue below joins the workers and, on
+  // failure, frees the proofs already assembled (a failed call returns none)
+  auto run_waves = [&]() -> int {
+  int rc = FRIEDA_OK;
   CU(cudaMemsetAsync(at<int>(ctx, pl.o_err), 0, sizeof(int), ctx->stream));
   // uploads run on the copy stream, one wave ahead of compute
   CU(cudaEventRecord(ctx->ev_free[0], ctx->stream));
@@ -991,6 +995,20 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     }
     ctx->last = w;
     ctx->have_last = true;
+  }
+  return FRIEDA_OK;
+  };
+  const int rc_waves = run_waves();
+  if (rc_waves != FRIEDA_OK) {
+    const std::string keep = ctx->err;
+    workers.join(0);
+    workers.join(1);
+    for (size_t i = 0; i < n; i++) {
+      if (proofs_out[i]) frieda_proof_free(proofs_out[i]);
+      proofs_out[i] = nullptr;
+    }
+    ctx->err = keep;
+    return rc_waves;
   }
   return fail_code();
 }
