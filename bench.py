@@ -572,13 +572,19 @@ def extras(ctx, host_np, cfg, torch):
     c4 = F.PcsConfig(CFG[0], CFG[1], 64, CFG[3])
     seeds = list(range(npv))
     ctx.prove_batch(blobs[:npv], seeds, c4)  # warm-up at the same size (workspace allocation)
+    # the per-kernel breakdown comes from a separate, instrumented call (two CUDA events around every launch); the
+    # rate is timed on plain calls (median of three wall-clock measurements of the whole synchronous call)
     ctx.profile_read(reset=True)
     ctx.set_profiling(True)
-    t0 = time.perf_counter()
-    roots, proofs = ctx.prove_batch(blobs[:npv], seeds, c4)
-    dt = time.perf_counter() - t0
+    ctx.prove_batch(blobs[:npv], seeds, c4)
     ctx.set_profiling(False)
     prof = ctx.profile_read(reset=True)
+    dts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        roots, proofs = ctx.prove_batch(blobs[:npv], seeds, c4)
+        dts.append(time.perf_counter() - t0)
+    dt = sorted(dts)[1]
     ok = all(F.verify_proof(proofs[i], seeds[i]) for i in (0, npv // 2, npv - 1))
     # GPU batch verification of those proofs next to the host verifier
     many = (proofs * ((4096 + npv - 1) // npv))[:4096]
@@ -618,7 +624,8 @@ def extras(ctx, host_np, cfg, torch):
     out["prove_c4_e2e"] = {"blobs": npv, "n_queries": 64, "pow_bits": CFG[3], "blobs_per_s": npv / dt,
                            "proofs_verify": ok, "wall_ms": dt * 1e3,
                            "kernel_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
-                           "note": "commit + FRI + grind + decommit + host proof assembly, kept trees"}
+                           "note": "commit + FRI + grind + decommit + host proof assembly, kept trees; wall = median of 3 plain "
+                                   "calls, kernel_ms from a separate instrumented call"}
     return out
 
 
