@@ -723,14 +723,13 @@ struct ProveHostBuf {  // every pointer into the wave's pinned readback buffer
 bool assemble_wave(const ProveHostBuf &hb, size_t b0, size_t nb, const Geom &g, uint32_t nq,
                    const frieda_pcs_config *cfg, uint8_t *roots_out, frieda_proof **proofs_out) {
   const uint32_t L = g.n_layers;
-  std::atomic<bool> oom{false};
-  auto assemble = [&](size_t b) {
+  // Phase 1, ONE thread: every allocation of the wave (~47 per proof).  Allocating from several short-lived threads
+  // measured 4 ms per 128 proofs on 4 threads and 5.8 ms on 16: each thread grows its own malloc arena (mprotect
+  // under the process's mmap lock), and that serialises against the page faults of the copies.
+  for (size_t b = 0; b < nb; b++) {
     frieda_proof *pr = (frieda_proof *)std::calloc(1, sizeof(frieda_proof));
-    if (!pr) {
-      oom = true;
-      return;
-    }
-    proofs_out[b0 + b] = pr;
+    if (!pr) return false;
+    proofs_out[b0 + b] = pr;  // (a failed call frees whatever hangs off the proofs it has created: prove_impl)
     pr->pcs_config = *cfg;
     pr->log_size_bound = g.p;
     pr->proof_of_work = hb.best[b];
@@ -740,45 +739,46 @@ bool assemble_wave(const ProveHostBuf &hb, size_t b0, size_t nb, const Geom &g, 
     pr->last_layer_poly = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) << g.log_last);
     pr->n_evaluations = hb.nuniq[b];
     pr->evaluations = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (hb.nuniq[b] ? hb.nuniq[b] : 1));
-    if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations) {
-      oom = true;
-      return;
-    }
-    std::memcpy(pr->last_layer_poly, &hb.last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
-    std::memcpy(pr->evaluations, &hb.evals[b * nq], sizeof(frieda_qm31) * hb.nuniq[b]);
+    if (!pr->inner_layers || !pr->last_layer_poly || !pr->evaluations) return false;
     for (uint32_t l = 0; l < L; l++) {
       frieda_layer_proof *lp = l == 0 ? &pr->first_layer : &pr->inner_layers[l - 1];
-      size_t ci = (b * L + l) * 2;
-      std::memcpy(lp->commitment, &hb.roots[(b * L + l) * 32], 32);
+      const size_t ci = (b * L + l) * 2;
       lp->n_fri_witness = hb.counts[ci];
       lp->n_hash_witness = hb.counts[ci + 1];
       lp->n_column_witness = 0;
       lp->fri_witness = (frieda_qm31 *)std::malloc(sizeof(frieda_qm31) * (lp->n_fri_witness ? lp->n_fri_witness : 1));
       lp->hash_witness = (uint8_t *)std::malloc(32 * (size_t)(lp->n_hash_witness ? lp->n_hash_witness : 1));
       lp->column_witness = (uint32_t *)std::malloc(4);
-      if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness) {
-        oom = true;
-        return;
-      }
+      if (!lp->fri_witness || !lp->hash_witness || !lp->column_witness) return false;
+    }
+  }
+  // Phase 2, a few threads: the copies (130 KB per proof, first touch of the new pages)
+  auto fill = [&](size_t b) {
+    frieda_proof *pr = proofs_out[b0 + b];
+    std::memcpy(pr->last_layer_poly, &hb.last[b << g.log_last], sizeof(frieda_qm31) << g.log_last);
+    std::memcpy(pr->evaluations, &hb.evals[b * nq], sizeof(frieda_qm31) * hb.nuniq[b]);
+    for (uint32_t l = 0; l < L; l++) {
+      frieda_layer_proof *lp = l == 0 ? &pr->first_layer : &pr->inner_layers[l - 1];
+      const size_t ci = (b * L + l) * 2;
+      std::memcpy(lp->commitment, &hb.roots[(b * L + l) * 32], 32);
       std::memcpy(lp->fri_witness, hb.fri + hb.offsets[ci] * sizeof(QM31), sizeof(QM31) * lp->n_fri_witness);
       std::memcpy(lp->hash_witness, hb.hash + hb.offsets[ci + 1] * 32, 32 * (size_t)lp->n_hash_witness);
     }
     if (roots_out) std::memcpy(roots_out + (b0 + b) * 32, &hb.roots[b * L * 32], 32);
   };
-  // proofs are independent: a few host threads
   unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()),
                                            std::min<size_t>(8, (nb + 31) / 32));
   if (nt <= 1) {
-    for (size_t b = 0; b < nb; b++) assemble(b);
+    for (size_t b = 0; b < nb; b++) fill(b);
   } else {
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++)
       th.emplace_back([&, t]() {
-        for (size_t b = t; b < nb; b += nt) assemble(b);
+        for (size_t b = t; b < nb; b += nt) fill(b);
       });
     for (auto &x : th) x.join();
   }
-  return !oom;
+  return true;
 }
 
 // ---- prove -------------------------------------------------------------------------------
