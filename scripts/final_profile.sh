@@ -13,8 +13,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${R}_benc
 # 2. launch list of the bench command (per-launch times are cold-cache and serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches.csv \
   python bench.py --steps 1 --warmup 3 --blobs 512 --no-cpu-baseline --no-passes > $O/ncu_bench.log 2>&1; echo "ncu list exit $?"
-# 3. full captures: second FRI-commit wave of 296 blobs (the first is warm-up), the LDE pass, one grind launch
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:merkle_bottom_kernel -s 17 -c 17 -f \
+# 3. full captures: second FRI-commit wave of 296 blobs (the first is warm-up; 16 merkle_bottom launches per wave:
+#    columns, circle fold, 7 line folds, 7 middle passes), the LDE pass, one grind launch
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:merkle_bottom_kernel -s 16 -c 16 -f \
   -o $O/${R}_merkle_bottom python scripts/prof_target.py 296 > $O/ncu_m.log 2>&1; echo "ncu merkle exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lde_warp_kernel -s 1 -c 1 -f \
   -o $O/${R}_lde_c2 python scripts/prof_target.py 256 > $O/ncu_l.log 2>&1; echo "ncu lde exit $?"
