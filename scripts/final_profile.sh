@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end GPU record (one B200): bench line, ncu launch list of the same command, `ncu --set full` captures of the
 # dominant kernels, criterion table, single-blob latency, compute-sanitizer passes.  Run under gpurun from the repo root:
-#   gpurun --timeout 2400 -- 'bash scripts/final_profile.sh r02'
+#   gpurun --timeout 2400 -- 'bash scripts/final_profile.sh r02'      (SKIP_NCU=1: everything but the ncu passes;
+#   the .ncu-rep files of one full run come to ~70 MB, above what gpurun merges back: fetch them in two calls)
 set -u
 R=${1:-r02}
 O=gpurun_out
@@ -10,6 +11,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 # 1. the bench line (never under a profiler)
 timeout 900 python bench.py --steps 3 --warmup 3 > $O/${R}_bench_1gpu.json 2> $O/${R}_bench_1gpu.err; echo "bench exit $?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${R}_bench_reference.json 2>/dev/null; echo "reference arm exit $?"
+if [ -z "${SKIP_NCU:-}" ]; then
 # 2. launch list of the bench command (per-launch times are cold-cache and serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches.csv \
   python bench.py --steps 1 --warmup 3 --blobs 512 --no-cpu-baseline --no-passes > $O/ncu_bench.log 2>&1; echo "ncu list exit $?"
@@ -25,6 +27,7 @@ python scripts/ncu_summary.py $O/${R}_merkle_bottom.ncu-rep $O/${R}_lde_c2.ncu-r
 rm -f $O/${R}_ncu_metrics.json
 python scripts/ncu_summary.py --json $O/${R}_ncu_metrics.json --blobs 296 --git "$(cat $O/../.git_head 2>/dev/null || echo unknown)" \
   $O/${R}_merkle_bottom.ncu-rep > $O/ncu_json.log 2>&1
+fi
 # 4. the reference's criterion groups and single-call latencies
 timeout 600 python benches/run.py --seconds 0.5 > $O/${R}_criterion.txt 2>&1; echo "criterion exit $?"
 timeout 300 python scripts/latency_probe.py > $O/${R}_latency.txt 2>&1
