@@ -245,6 +245,38 @@ def test_lde_linearity_full_size(ctx, torch_mod):
     assert ev.max() < P
 
 
+def oracle_merkle_root(cols_b):
+    """Root of the tree over one blob's (4, n) columns with the oracle's compression (hash_node)."""
+    n = cols_b.shape[1]
+    level = [O.blake2s_compress([0] * 8, [int(cols_b[c, i]) for c in range(4)] + [0] * 12) for i in range(n)]
+    while len(level) > 1:
+        level = [O.blake2s_compress([0] * 8, list(level[2 * i]) + list(level[2 * i + 1])) for i in range(len(level) // 2)]
+    return np.array(level[0], dtype="<u4").tobytes()
+
+
+@pytest.mark.parametrize("log,n_blobs", [(12, 3), (14, 1), (15, 2), (16, 1)])
+def test_merkle_pass_latency_form_shapes(ctx, torch_mod, log, n_blobs):
+    # a few blobs = the latency form of the Merkle passes (merkle.cu): chunks of 128 / 256 leaves in 128-thread CTAs
+    # (in-place reduction by rounds), 512-leaf chunks in 256-thread CTAs; truncated and kept trees must give the
+    # oracle's root
+    torch = torch_mod
+    rng = np.random.default_rng(1000 + log)
+    cols = rng.integers(0, P, (n_blobs, 4, 1 << log), dtype=np.uint32)
+    d_cols = torch.from_numpy(cols.view(np.int32)).cuda()
+    want = [oracle_merkle_root(cols[b]) for b in range(n_blobs)]
+    for keep in (False, True):
+        d_roots = torch.zeros((n_blobs, 32), dtype=torch.uint8, device="cuda")
+        d_tree = torch.zeros((n_blobs, 2 << log, 32), dtype=torch.uint8, device="cuda") if keep else None
+        torch.cuda.synchronize()
+        ctx.pass_merkle(d_cols.data_ptr(), log, n_blobs, d_tree.data_ptr() if keep else None, d_roots.data_ptr())
+        torch.cuda.ExternalStream(ctx.stream_ptr).synchronize()
+        roots = d_roots.cpu().numpy()
+        for b in range(n_blobs):
+            assert roots[b].tobytes() == want[b], (log, b, keep)
+            if keep:
+                assert d_tree[b, 1].cpu().numpy().tobytes() == want[b]
+
+
 @pytest.mark.parametrize("log", [0, 1, 2, 5, 9, 10, 11, 13, 21])
 def test_merkle_pass_vs_oracle(ctx, torch_mod, log):
     torch = torch_mod
