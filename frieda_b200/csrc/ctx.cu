@@ -967,8 +967,10 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
     hb.err_flag = reinterpret_cast<const int *>(hpin + h_err);
     hb.fri = hpin + h_wit;
     hb.hash = hpin + h_wit + fri_pad;
+    // (two pieces: the alignment gap between them is never written on the device)
     if (last_wave) {
-      cp(h_wit, d_gather, fri_pad + hash_bytes, ctx->stream);
+      cp(h_wit, d_gather, fri_bytes, ctx->stream);
+      cp(h_wit + fri_pad, d_gather + fri_pad, hash_bytes, ctx->stream);
       tr.mark("write launch + readback enqueue");
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
       tr.mark("sync 2 (write+d2h)");
@@ -979,7 +981,8 @@ int prove_impl(frieda_ctx *ctx, const uint8_t *blobs, size_t len, size_t stride,
       // witnesses go back on the copy stream, behind the next wave's upload and under its compute
       if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_gathered[bi], ctx->stream);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_gathered[bi], 0);
-      cp(h_wit, d_gather, fri_pad + hash_bytes, ctx->copy_stream);
+      cp(h_wit, d_gather, fri_bytes, ctx->copy_stream);
+      cp(h_wit + fri_pad, d_gather + fri_pad, hash_bytes, ctx->copy_stream);
       if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_readback[bi], ctx->copy_stream);
       if (ce != cudaSuccess) return ctx->fail(ce, "proof readback", __LINE__);
       cudaEvent_t ev = ctx->ev_readback[bi];
